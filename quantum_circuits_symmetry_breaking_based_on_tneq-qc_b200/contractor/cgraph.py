@@ -1,0 +1,445 @@
+"""Contraction graph: the greedy schedule lowered to PAIRWISE real contractions.
+
+Input : a GreedySchedule (one multi-operand einsum per qubit group, exactly the
+        reference's bookkeeping, greedy_strategy.py:690-990).
+Output: a DAG of nodes over REAL tensors
+          input     a tensor handed in by the caller (core, state, Mx, grad seed)
+          contract  C = P o Q  (sum over the indices P and Q share)
+          lin       sparse linear map with <= 2 terms per destination element
+                    (complex conjugate, complex->2x2-real expansion, permute,
+                    and the adjoints of those)
+          seed      d(loss)/d(result) from the fused loss
+        plus, if gradients are requested, the reverse-mode adjoint nodes.
+
+Design points (DESIGN.md section "plan compiler"):
+  * batch symbols 'a'/'b' are not indices here: a node is either `batched`
+    (one value per sample) or shared.  Shared sub-trees (cores contracted with
+    circuit states, complex expansion of cores, ...) are batch independent and
+    end up in the one-off PREP section of the device program.
+  * complex tensors are real tensors with a trailing index of extent 2.
+    P o Q over complex numbers becomes ONE real contraction of P with the
+    2x2-real expansion of Q:  Qx[k,ri,n,ro] = E[ri,ro,c] Q[k,n,c]; so the device
+    only ever runs real arithmetic, and reverse mode in this representation
+    directly yields PyTorch's complex gradient convention dL/dRe + i dL/dIm.
+  * within a group the pairwise order is chosen by dynamic programming over
+    operand subsets minimising per-sample multiply-adds (shared o shared
+    products are nearly free); circuit states are folded into their core first.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .greedy_plan import GreedySchedule, Operand
+
+
+@dataclass
+class Node:
+    id: int
+    kind: str                       # input | contract | lin | seed
+    idx: Tuple[int, ...]            # index ids in memory order (compact row-major)
+    batched: bool
+    cplx: bool = False              # last index is the (re, im) pair of a complex tensor
+    needs_grad: bool = False
+    operand: Optional[Operand] = None       # input
+    p: int = -1                     # contract / lin source
+    q: int = -1
+    reduce_batch: bool = False      # contract of two batched tensors summed over samples
+    src_flat: Optional[np.ndarray] = None   # lin: [ndst, T] flat source positions
+    coef: Optional[np.ndarray] = None       # lin: [ndst, T]
+    acc_into: int = -1              # adjoint contribution accumulated into that node's buffer
+    is_accum: bool = False          # zero-initialised accumulation buffer (shared adjoints)
+    role: str = "fwd"               # fwd | adj
+    tag: str = ""
+
+
+class CGraph:
+    def __init__(self, complex_mode: bool):
+        self.complex_mode = complex_mode
+        self.dims: Dict[int, int] = {}
+        self.nodes: List[Node] = []
+        self.inputs: Dict[Tuple[str, object], List[int]] = {}
+        self.result: int = -1
+        self.result_batch: str = ""
+        self.seed: int = -1
+        self.grads: Dict[Tuple[str, object], int] = {}     # input key -> accum node (GOUT)
+        self.flops_per_sample = 0.0
+        self.flops_shared = 0.0
+
+    # ---- construction helpers ---------------------------------------------
+    def new_index(self, extent: int) -> int:
+        i = len(self.dims)
+        self.dims[i] = int(extent)
+        return i
+
+    def size(self, idx: Sequence[int]) -> int:
+        n = 1
+        for i in idx:
+            n *= self.dims[i]
+        return n
+
+    def shape(self, idx):
+        return tuple(self.dims[i] for i in idx)
+
+    def _add(self, **kw) -> Node:
+        n = Node(id=len(self.nodes), **kw)
+        self.nodes.append(n)
+        return n
+
+    def add_input(self, operand: Operand, idx, batched, needs_grad=False, cplx=False) -> Node:
+        n = self._add(kind="input", idx=tuple(idx), batched=batched, cplx=cplx, needs_grad=needs_grad,
+                      operand=operand)
+        return n
+
+    def add_contract(self, p: Node, q: Node, out_idx=None, reduce_batch=False, role="fwd", cplx=False) -> Node:
+        shared = [i for i in p.idx if i in q.idx]
+        if out_idx is None:
+            out_idx = [i for i in p.idx if i not in shared] + [i for i in q.idx if i not in shared]
+        batched = (p.batched or q.batched) and not reduce_batch
+        n = self._add(kind="contract", idx=tuple(out_idx), batched=batched, cplx=cplx,
+                      needs_grad=p.needs_grad or q.needs_grad, p=p.id, q=q.id,
+                      reduce_batch=reduce_batch, role=role)
+        work = float(self.size(set(p.idx) | set(q.idx)))
+        if p.batched or q.batched:
+            self.flops_per_sample += 2.0 * work
+        else:
+            self.flops_shared += 2.0 * work
+        return n
+
+    def add_lin(self, src: Node, dst_idx, src_flat, coef, role="fwd", cplx=False, batched=None) -> Node:
+        src_flat = np.asarray(src_flat, dtype=np.int64)
+        coef = np.asarray(coef, dtype=np.float64)
+        if src_flat.ndim == 1:
+            src_flat, coef = src_flat[:, None], coef[:, None]
+        assert src_flat.shape == coef.shape and src_flat.shape[0] == self.size(dst_idx)
+        return self._add(kind="lin", idx=tuple(dst_idx), batched=src.batched if batched is None else batched,
+                         cplx=cplx, needs_grad=src.needs_grad, p=src.id, src_flat=src_flat, coef=coef, role=role)
+
+    # ---- elementary linear maps ---------------------------------------------
+    def _flat_of(self, idx_from, idx_to, fixed=None):
+        """For every element of a tensor laid out with index order `idx_to`, the
+        flat position of the same element in layout `idx_from`; indices of
+        idx_from missing from idx_to take their value from `fixed`."""
+        shp = self.shape(idx_to)
+        grids = np.indices(shp).reshape(len(shp), -1) if shp else np.zeros((0, 1), dtype=np.int64)
+        pos = {i: k for k, i in enumerate(idx_to)}
+        flat = np.zeros(grids.shape[1] if shp else 1, dtype=np.int64)
+        stride = 1
+        for i in reversed(idx_from):
+            v = grids[pos[i]] if i in pos else fixed[i]
+            flat = flat + v * stride
+            stride *= self.dims[i]
+        return flat
+
+    def lin_permute(self, src: Node, dst_idx, role="fwd") -> Node:
+        flat = self._flat_of(src.idx, dst_idx)
+        return self.add_lin(src, dst_idx, flat, np.ones_like(flat, dtype=np.float64), role=role, cplx=src.cplx)
+
+    def lin_conj(self, src: Node) -> Node:
+        assert src.cplx
+        flat = np.arange(self.size(src.idx), dtype=np.int64)
+        coef = np.where(flat % 2 == 0, 1.0, -1.0)
+        return self.add_lin(src, src.idx, flat, coef, cplx=True)
+
+    def lin_expand(self, src: Node, ri_in: int, ro: int) -> Node:
+        """Qx[x..., ri, ro] = E[ri, ro, c] Q[x..., c] with E the 2x2 real form of a
+        complex scalar: [[re, im], [-im, re]] (rows ri, columns ro)."""
+        assert src.cplx
+        body = src.idx[:-1]
+        n = self.size(body)
+        base = np.arange(n, dtype=np.int64)[:, None] * 2                  # position of (x, c=0)
+        c_of = np.array([0, 1, 1, 0], dtype=np.int64)[None, :]           # (ri,ro) -> c
+        sg = np.array([1.0, 1.0, -1.0, 1.0])[None, :]
+        flat = (base + c_of).reshape(-1)
+        coef = np.broadcast_to(sg, (n, 4)).reshape(-1)
+        return self.add_lin(src, tuple(body) + (ri_in, ro), flat, coef, cplx=False)
+
+    # ---- complex-aware contraction -------------------------------------------
+    def contract(self, p: Node, q: Node) -> Node:
+        if not self.complex_mode:
+            return self.add_contract(p, q)
+        assert p.cplx and q.cplx
+        # expand the operand that plays the "matrix" role: shared beats batched, small beats big
+        def weight(n):
+            return (1 if n.batched else 0, self.size(n.idx))
+        x, y = (q, p) if weight(q) <= weight(p) else (p, q)
+        ro = self.new_index(2)
+        xx = self.lin_expand(x, y.idx[-1], ro)
+        shared = [i for i in y.idx if i in xx.idx]
+        out = [i for i in y.idx if i not in shared] + [i for i in xx.idx if i not in shared and i != ro] + [ro]
+        return self.add_contract(y, xx, out_idx=out, cplx=True)
+
+
+# ----------------------------------------------------------------------------
+# pairwise order inside one greedy group
+# ----------------------------------------------------------------------------
+def _pairwise_order(index_sets, batched, out_set, dims):
+    """Return a list of (i, j) merges over a growing operand list (opt_einsum
+    'path' convention is avoided: positions refer to an append-only list).
+    Minimises sum of per-contraction multiply-adds; shared o shared costs 1e-6x."""
+    n = len(index_sets)
+    if n == 1:
+        return []
+
+    def extent(s):
+        v = 1.0
+        for i in s:
+            v *= dims[i]
+        return v
+
+    if n <= 12:
+        full = (1 << n) - 1
+        cover = {}
+        for m in range(1, full + 1):
+            inside = set()
+            for k in range(n):
+                if m >> k & 1:
+                    inside |= index_sets[k]
+            cover[m] = inside
+        res, isb = {}, {}
+        for m in range(1, full + 1):
+            outside = set(out_set)
+            for k in range(n):
+                if not m >> k & 1:
+                    outside |= index_sets[k]
+            res[m] = frozenset(i for i in cover[m] if i in outside)
+            isb[m] = any(batched[k] for k in range(n) if m >> k & 1)
+        best = {1 << k: (0.0, None) for k in range(n)}
+        for size in range(2, n + 1):
+            for combo in itertools.combinations(range(n), size):
+                m = 0
+                for k in combo:
+                    m |= 1 << k
+                low = m & -m
+                sub = (m - 1) & m
+                cand = None
+                while sub:
+                    if sub & low:
+                        rest = m ^ sub
+                        if rest and sub in best and rest in best:
+                            a, b = res[sub], res[rest]
+                            connected = bool(a & b)
+                            cost = extent(a | b) * (1.0 if (isb[sub] or isb[rest]) else 1e-6)
+                            if not connected:
+                                cost *= 1e3  # outer products only as a last resort
+                            tot = best[sub][0] + best[rest][0] + cost
+                            if cand is None or tot < cand[0]:
+                                cand = (tot, (sub, rest))
+                    sub = (sub - 1) & m
+                if cand is not None:
+                    best[m] = cand
+        merges, slot = [], {1 << k: k for k in range(n)}
+
+        def emit(m):
+            if m in slot:
+                return slot[m]
+            a, b = best[m][1]
+            ia, ib = emit(a), emit(b)
+            slot[m] = n + len(merges)
+            merges.append((ia, ib))
+            return slot[m]
+
+        emit(full)
+        return merges
+    # greedy fallback for very large groups
+    live = {k: (frozenset(index_sets[k]), batched[k]) for k in range(n)}
+    merges, nxt = [], n
+    while len(live) > 1:
+        pick = None
+        keys = list(live)
+        for x in range(len(keys)):
+            for y in range(x + 1, len(keys)):
+                a, b = live[keys[x]], live[keys[y]]
+                if not (a[0] & b[0]) and len(live) > 2:
+                    continue
+                c = extent(a[0] | b[0]) * (1.0 if (a[1] or b[1]) else 1e-6)
+                if pick is None or c < pick[0]:
+                    pick = (c, keys[x], keys[y])
+        if pick is None:
+            pick = (0.0, keys[0], keys[1])
+        _, kx, ky = pick
+        a, b = live.pop(kx), live.pop(ky)
+        others = set(out_set)
+        for v in live.values():
+            others |= v[0]
+        live[nxt] = (frozenset(i for i in (a[0] | b[0]) if i in others), a[1] or b[1])
+        merges.append((kx, ky))
+        nxt += 1
+    return merges
+
+
+def build_forward(schedule: GreedySchedule, complex_mode: bool, core_shapes: Dict[object, Tuple[int, ...]],
+                  trainable: Sequence[Tuple[str, object]] = ()) -> CGraph:
+    """Lower the schedule.  core_shapes: ('core'|'rcore', name) -> dims.
+    `trainable`: input keys ('core', name) / ('rcore', name) that require gradients.
+
+    Index ids are GLOBAL: one id per network edge (the schedule's raw symbols), so
+    a tensor produced at one qubit is consumed later without any relabelling.  A
+    core that occurs as its L copy and as its R copy is two input nodes over the
+    same caller buffer (their gradients accumulate into one output buffer)."""
+    g = CGraph(complex_mode)
+    trainable = set(trainable)
+    edge_id: Dict[str, int] = {}
+    produced: Dict[int, Node] = {}
+    want_order: Dict[int, List[int]] = {}
+
+    def ids_of(symbols, dims):
+        out = []
+        for c in symbols:
+            if c not in edge_id:
+                edge_id[c] = g.new_index(dims[c])
+            out.append(edge_id[c])
+        return out
+
+    for step in schedule.steps:
+        nodes, state_pos = [], []
+        for sub, op in zip(step.raw_subs, step.operands):
+            body = [c for c in sub if c not in "ab"]
+            ids = ids_of(body, step.raw_dims)
+            if op.kind == "tmp":
+                n = produced[op.key]
+                have = n.idx[:-1] if n.cplx else n.idx
+                assert sorted(have) == sorted(ids), "tmp operand does not carry the expected edges"
+            else:
+                key = ("core", op.key) if op.kind in ("core", "core_conj") else (op.kind, op.key)
+                if key[0] in ("core", "rcore"):
+                    if tuple(core_shapes[key]) != tuple(g.dims[i] for i in ids):
+                        raise ValueError(f"core {op.key!r}: shape {tuple(core_shapes[key])} does not match its "
+                                         f"edges {tuple(g.dims[i] for i in ids)}")
+                idx = list(ids) + ([g.new_index(2)] if complex_mode else [])
+                n = g.add_input(Operand(key[0], key[1]), idx, batched=any(c in "ab" for c in sub),
+                                needs_grad=key in trainable, cplx=complex_mode)
+                g.inputs.setdefault(key, []).append(n.id)
+                if op.kind == "core_conj" and complex_mode:
+                    n = g.lin_conj(n)
+                if op.kind == "state":
+                    state_pos.append(len(nodes))
+            nodes.append(n)
+        out_ids = ids_of([c for c in step.raw_out if c not in "ab"], step.raw_dims)
+        # fold circuit states into the tensor that carries their edge
+        alive = {k: n for k, n in enumerate(nodes) if k not in state_pos}
+        for k in state_pos:
+            edge = nodes[k].idx[0]
+            host = next((h for h, n in alive.items() if edge in n.idx), None)
+            if host is None:
+                alive[k] = nodes[k]
+            else:
+                alive[host] = g.contract(alive[host], nodes[k])
+        live = [alive[k] for k in sorted(alive)]
+        sets = [set(n.idx[:-1] if n.cplx else n.idx) for n in live]
+        for i in set().union(*sets):
+            if sum(i in s for s in sets) == 1 and i not in out_ids:
+                raise NotImplementedError("an edge that is summed without a partner is not supported")
+        pool = list(live)
+        for a, b in _pairwise_order(sets, [n.batched for n in live], set(out_ids), g.dims):
+            pool.append(g.contract(pool[a], pool[b]))
+        res = pool[-1]
+        res.tag = f"step{step.out}"
+        produced[step.out] = res
+        want_order[step.out] = out_ids
+    if schedule.result.kind != "tmp":
+        raise RuntimeError("nothing to contract: the network is a single tensor")
+    res = produced[schedule.result.key]
+    want = want_order[schedule.result.key]
+    if list(res.idx[:-1] if res.cplx else res.idx) != want:
+        res = g.lin_permute(res, tuple(want) + ((res.idx[-1],) if res.cplx else ()))
+    if res.kind == "input":
+        res = g.lin_permute(res, res.idx)      # single-operand network: plain copy
+    g.result = res.id
+    g.result_batch = "".join(c for c in "ab" if any(c in sub for st in schedule.steps for sub in st.raw_subs))
+    return g
+
+
+# ----------------------------------------------------------------------------
+# reverse mode
+# ----------------------------------------------------------------------------
+def add_backward(g: CGraph, seed_from: str):
+    """Append adjoint nodes.  seed_from: 'input' (d result supplied by the caller,
+    autograd route) or 'loss' (fused clamp/log/mean loss, engine_siamese.py:490-530).
+
+    Batched tensors have exactly one consumer, so their adjoint is one node.
+    Shared tensors (cores and everything derived from them in PREP) may have
+    several; their adjoints are zero-initialised accumulation buffers that every
+    contribution adds into.  All occurrences of one caller tensor share ONE
+    accumulation buffer (g.grads[key]): that buffer is the returned gradient."""
+    res = g.nodes[g.result]
+    if seed_from == "input":
+        seed = g.add_input(Operand("gradseed", 0), res.idx, True, cplx=res.cplx)
+        g.inputs[("gradseed", 0)] = [seed.id]
+    else:
+        seed = g._add(kind="seed", idx=res.idx, batched=True, cplx=res.cplx, p=res.id, role="adj")
+    g.seed = seed.id
+    adj: Dict[int, Node] = {res.id: seed}
+    accum: Dict[object, Node] = {}
+
+    def accum_for(target: Node) -> Node:
+        key = ("in",) + (target.operand.kind, target.operand.key) if target.kind == "input" else ("node", target.id)
+        if key not in accum:
+            accum[key] = g._add(kind="lin", idx=target.idx, batched=False, cplx=target.cplx, is_accum=True,
+                                role="adj", tag=f"accum:{key}")
+            if target.kind == "input":
+                g.grads[(target.operand.kind, target.operand.key)] = accum[key].id
+        return accum[key]
+
+    def adjoint_of(node: Node) -> Optional[Node]:
+        if node.batched:
+            return adj.get(node.id)
+        key = ("node", node.id)
+        return accum.get(key)
+
+    def contribute(target: Node, make):
+        if target.batched:
+            assert target.id not in adj, "a batched tensor with two consumers is not supported"
+            adj[target.id] = make(-1)
+        else:
+            make(accum_for(target).id)
+
+    n_fwd = len(g.nodes)
+    for node in reversed(g.nodes[:n_fwd]):
+        if not node.needs_grad or node.kind in ("input", "seed") or node.role != "fwd":
+            continue
+        gnode = adjoint_of(node)
+        if gnode is None:
+            continue
+        if node.kind == "contract":
+            p, q = g.nodes[node.p], g.nodes[node.q]
+            for me, other in ((p, q), (q, p)):
+                if not me.needs_grad:
+                    continue
+
+                def make(acc, me=me, other=other):
+                    red = (not me.batched) and (gnode.batched or other.batched)
+                    c = g.add_contract(gnode, other, out_idx=me.idx, reduce_batch=red, role="adj", cplx=me.cplx)
+                    c.acc_into, c.needs_grad = acc, False
+                    return c
+
+                contribute(me, make)
+        elif node.kind == "lin":
+            src = g.nodes[node.p]
+
+            def make(acc, src=src, node=node):
+                nsrc = g.size(src.idx)
+                rows = [[] for _ in range(nsrc)]
+                for d in range(node.src_flat.shape[0]):
+                    for t in range(node.src_flat.shape[1]):
+                        if node.coef[d, t] != 0.0:
+                            rows[int(node.src_flat[d, t])].append((d, float(node.coef[d, t])))
+                width = max(1, max(len(r) for r in rows))
+                assert width <= 2, "adjoint of a linear map with more than two terms"
+                sf = np.zeros((nsrc, width), dtype=np.int64)
+                cf = np.zeros((nsrc, width), dtype=np.float64)
+                for j, r in enumerate(rows):
+                    for t, (d, c) in enumerate(r):
+                        sf[j, t], cf[j, t] = d, c
+                c = g.add_lin(gnode, src.idx, sf, cf, role="adj", cplx=src.cplx, batched=gnode.batched)
+                c.acc_into, c.needs_grad = acc, False
+                return c
+
+            contribute(src, make)
+    for key, ids in g.inputs.items():
+        if g.nodes[ids[0]].needs_grad and key not in g.grads:
+            raise RuntimeError(f"no gradient path to {key}")
+    return g

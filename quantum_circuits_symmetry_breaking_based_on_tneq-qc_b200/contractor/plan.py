@@ -1,0 +1,89 @@
+"""ContractionPlan: everything that can be decided before seeing a batch.
+
+Built once per (graph, operand signature, dtype) and cached by the strategy:
+the symbolic greedy schedule (bit-exact reference bookkeeping), the pairwise
+contraction graph, and the lowered device programs
+
+    'fwd'    probabilities / amplitudes          (contract_with_compiled_strategy)
+    'bwd'    reverse sweep seeded by autograd    (torch.autograd route through compute_fn)
+    'train'  forward + fused loss + reverse sweep (contract_with_compiled_strategy_for_gradient)
+
+The reference rebuilds the equivalent bookkeeping on every call
+(greedy_strategy.py:45-598).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from . import cgraph, vm_program
+from .greedy_plan import GreedySchedule, build_schedule
+
+
+def signature_of(nqubits, circuit_states, measure_matrices):
+    """(state_dims, mx_info) with the reference's presence rules
+    (greedy_strategy.py:108-158): containers may be None, dict, list or tuple;
+    list entries past the end and None measurements are simply absent."""
+
+    def present(container, q):
+        if container is None:
+            return False
+        if isinstance(container, dict):
+            return q in container
+        if isinstance(container, (list, tuple)):
+            return q < len(container)
+        return True
+
+    state_dims, mx_info = {}, {}
+    for q in range(nqubits):
+        if present(circuit_states, q):
+            state_dims[q] = int(circuit_states[q].shape[0])
+        if present(measure_matrices, q) and measure_matrices[q] is not None:
+            m = measure_matrices[q]
+            bsym = "a" if m.ndim == 3 else ("ab" if m.ndim == 4 else "")
+            mx_info[q] = (bsym, int(m.shape[-2]), int(m.shape[-1]))
+    return state_dims, mx_info
+
+
+class ContractionPlan:
+    def __init__(self, adjacency_table, nqubits: int, core_shapes: Dict[str, Tuple[int, ...]],
+                 state_dims: Dict[int, int], mx_info: Dict[int, Tuple[str, int, int]], dtype: str,
+                 right="symmetric", right_table=None, right_core_shapes=None,
+                 trainable: Optional[Sequence[Tuple[str, object]]] = None):
+        """dtype: 'float32' | 'float64' | 'complex64' | 'complex128'."""
+        self.nqubits = nqubits
+        self.dtype = dtype
+        self.complex_mode = dtype.startswith("complex")
+        self.real_dtype = "f32" if dtype in ("float32", "complex64") else "f64"
+        self.schedule: GreedySchedule = build_schedule(adjacency_table, nqubits, state_dims, mx_info,
+                                                       right=right, right_table=right_table)
+        self.core_shapes = {("core", k): tuple(v) for k, v in core_shapes.items()}
+        for k, v in (right_core_shapes or {}).items():
+            self.core_shapes[("rcore", k)] = tuple(v)
+        if trainable is None:
+            trainable = list(self.core_shapes)
+        self.trainable = list(trainable)
+        self.nb = 2 if any(b == "ab" for b, _, _ in mx_info.values()) else 1
+        self.mx_batch = {q: b for q, (b, _, _) in mx_info.items()}
+        self._graphs: Dict[str, cgraph.CGraph] = {}
+        self._programs: Dict[str, vm_program.VMProgram] = {}
+
+    @property
+    def equations(self) -> List[str]:
+        return self.schedule.equations
+
+    def graph(self, mode: str) -> cgraph.CGraph:
+        key = "fwd" if mode == "fwd" else mode
+        if key not in self._graphs:
+            g = cgraph.build_forward(self.schedule, self.complex_mode, self.core_shapes,
+                                     trainable=() if mode == "fwd" else self.trainable)
+            if mode == "bwd":
+                cgraph.add_backward(g, "input")
+            elif mode == "train":
+                cgraph.add_backward(g, "loss")
+            self._graphs[key] = g
+        return self._graphs[key]
+
+    def program(self, mode: str) -> vm_program.VMProgram:
+        if mode not in self._programs:
+            self._programs[mode] = vm_program.lower(self.graph(mode), mode, self.real_dtype, nb=self.nb)
+        return self._programs[mode]
