@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the QCTN contraction hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  Metric (BASELINE.json): samples/sec for the QCTN
+forward+backward contraction.  Workloads:
+
+  cfg3 (default)  training step (forward + loss + reverse sweep, + NCCL gradient all-reduce
+                  when N > 1) of the 24-qubit two-layer merged MPS network, K=3, float32,
+                  GLOBAL batch 16384 split over the N GPUs (strong scaling)
+  cfg2            forward probabilities, 16-qubit MPS, K=3, batch 4096
+  cfg2-large      the same with batch 2^20 (bandwidth/compute visible above launch latency)
+
+A "step" is one pass of the hot path over one batch of synthetic measurements
+(x ~ N(0,1), torch.manual_seed(42); cores QR-orthogonal, torch.manual_seed(1234); states
+e_{K-1}; Mx = TNTensor-normalised Hermite-function outer products).
+
+`value`  : device-resident inputs, CUDA-event timed per step on the launching stream, L2
+           flushed between timed steps, max over ranks.
+`e2e`    : the same step through the public engine API with the batch's measurement
+           matrices in PINNED HOST memory: host->device copy and the device->host read of the
+           loss are inside the timed region.
+`--impl reference`: the reference's own CPU algorithm (oracle port of GreedyStrategy +
+           torch.autograd, bit-identical to /root/reference on CPU, see oracle/) on the box's host
+           cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg3": dict(kind="merged", n=24, K=3, batch=16384, mode="train", dtype="float32",
+                 name="cfg3: 24-qubit 2-layer merged MPS QCTN, K=3, fwd+loss+bwd, global batch 16384"),
+    "cfg2": dict(kind="mps", n=16, K=3, batch=4096, mode="fwd", dtype="float32",
+                 name="cfg2: 16-qubit MPS QCTN, K=3, forward probabilities, batch 4096"),
+    "cfg2-large": dict(kind="mps", n=16, K=3, batch=1 << 20, mode="fwd", dtype="float32",
+                       name="cfg2-large: 16-qubit MPS QCTN, K=3, forward probabilities, batch 2^20"),
+    "cfg2-train": dict(kind="mps", n=16, K=3, batch=1 << 18, mode="train", dtype="float32",
+                       name="16-qubit MPS QCTN, K=3, fwd+loss+bwd, batch 2^18"),
+}
+
+
+def build_graph(tb, kind, n, K):
+    g = tb.QCTNHelper.generate_example_graph(n=n, graph_type="mps" if kind == "merged" else kind, dim_char=str(K))
+    if kind == "merged":
+        q = tb.QCTN(g)
+        return tb.QCTN.merge(q, q).graph
+    return g
+
+
+def synth_inputs(graph, K, B, dtype):
+    """CPU tensors, seeded as SURVEY 8(d) prescribes (oracle helpers: test infrastructure only)."""
+    import torch
+    from oracle import qctn_oracle as oc
+    names, table, nq = oc.parse_graph(graph)
+    torch.manual_seed(1234)
+    cores = oc.random_cores(table, getattr(torch, dtype))
+    torch.manual_seed(42)
+    x = torch.randn(B, nq)
+    return names, table, nq, cores, x
+
+
+class ClockSampler:
+    """nvidia-smi sampling while the timed region runs (B200_PROFILING.md, clocks line)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_reference(args, wl):
+    """--impl reference / cpu_baseline: the oracle (reference algorithm) on host cores."""
+    import torch
+    import tneq_b200 as tb
+    from oracle import qctn_oracle as oc
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    graph = build_graph(tb, wl["kind"], wl["n"], wl["K"])
+    names, table, nq, cores, x_all = synth_inputs(graph, wl["K"], 4096, wl["dtype"])
+    states = oc.unit_states(nq, wl["K"])
+    n_steps = args.steps if args.impl == "reference" else 3
+    n_warm = max(1, args.warmup) if args.impl == "reference" else 1
+
+    def run_once(xb):
+        mx, _ = oc.generate_data(xb, wl["K"], torch.float32, "TNTensor")  # fresh: auto_scale is in place
+        t0 = time.perf_counter()
+        if wl["mode"] == "train":
+            oc.loss_and_grads(graph, cores, states, mx)
+        else:
+            with torch.no_grad():
+                oc.forward(graph, cores, states, mx)
+        return time.perf_counter() - t0
+
+    if args.ref_batch:
+        sample_b = args.ref_batch
+    else:
+        # bounded sample: probe the cost at a tiny batch, then size the batch so that the whole
+        # warmup + steps run takes about `budget` seconds (left-to-right einsum intermediates make
+        # the two-layer network cost ~1 s per sample on 8 cores)
+        budget = 90.0 if args.impl == "reference" else 20.0
+        t2 = run_once(x_all[:2])
+        t2 = min(t2, run_once(x_all[:2]))
+        per_sample = max(t2 / 2, 1e-6)
+        sample_b = int(max(1, min(4096, budget / ((n_steps + n_warm) * per_sample))))
+    x = x_all[:sample_b]
+    def step():
+        return run_once(x)
+
+    for _ in range(n_warm):
+        step()
+    times = [step() for _ in range(n_steps)]
+    total = sum(times)
+    val = sample_b * len(times) / total
+    return dict(value=val, unit="samples/s", cores=threads, kind="port",
+                sample=f"{len(times)} steps of batch {sample_b} of the same network ({wl['mode']}), "
+                       f"oracle port of the reference CPU path (bit-identical to /root/reference on CPU)",
+                ms_per_step=1e3 * total / len(times), batch=sample_b)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's global batch")
+    ap.add_argument("--ref-batch", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ref = time_reference(args, wl)
+        line = {"impl": "reference", "metric": "samples/sec for QCTN fwd+bwd contraction", "value": ref["value"],
+                "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ref["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "reference_sample_batch": ref["batch"]},
+                "cpu_baseline": {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": ref["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import __graft_entry__ as ge
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
+    if rank == 0:
+        ge.build()                             # no-op when the in-tree library is current
+    if dist is not None:
+        dist.barrier()
+    import tneq_b200 as tb
+    from tneq_b200 import _lib
+    _lib.load()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    K, n = wl["K"], wl["n"]
+    graph = build_graph(tb, wl["kind"], n, K)
+    B_global = wl["batch"]
+    B = B_global // world                      # strong scaling: the global batch is fixed
+    names, table, nq, cores_cpu, x_cpu = synth_inputs(graph, K, B_global, wl["dtype"])
+    x_local = x_cpu[rank * B:(rank + 1) * B]
+
+    backend = tb.BackendFactory.create_backend("b200", device=str(dev), dtype=wl["dtype"])
+    engine = tb.EngineSiamese(backend=backend, strategy_mode="balanced", mx_K=K)
+    qctn = tb.QCTN(graph, backend=backend)
+    packed = torch.cat([cores_cpu[c].reshape(-1) for c in names]).to(dev)
+    if dist is not None:
+        dist.broadcast(packed, src=0)          # the reference forgets this
+    off = 0
+    for c in names:
+        cnt = cores_cpu[c].numel()
+        qctn.cores_weights[c] = packed[off:off + cnt].reshape(cores_cpu[c].shape).clone().requires_grad_(True)
+        off += cnt
+    states = [torch.zeros(K, device=dev) for _ in range(nq)]
+    for s in states:
+        s[-1] = 1.0
+    mx_dev, _ = engine.generate_data(x_local.to(dev), K=K, ret_type="TNTensor")
+    log_scale = sum(m.log_scale for m in mx_dev)
+    mx_dev = [tb.TNTensor(m.tensor.contiguous(), m.scale, m.log_scale) for m in mx_dev]
+    mx_host = [m.tensor.cpu().pin_memory() for m in mx_dev]
+    mx_scales = [(m.scale, m.log_scale) for m in mx_dev]
+    h2d_bytes = sum(m.numel() * m.element_size() for m in mx_host)
+
+    fn = engine._compiled(qctn, states, mx_dev, True, "symmetric")
+    cores_dict = {c: qctn.cores_weights[c] for c in names}
+    train = wl["mode"] == "train"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_device():
+        if train:
+            loss, grads, _vals, _sc = fn.loss_and_grads(cores_dict, states, mx_dev)
+            if dist is not None:
+                flat = torch.cat([g.reshape(-1) for g in grads] + [loss.reshape(1)])
+                dist.all_reduce(flat)
+                flat /= world
+            return loss
+        with torch.no_grad():
+            return fn(cores_dict, states, mx_dev).tensor
+
+    def step_e2e():
+        mxs = [tb.TNTensor(h.to(dev, non_blocking=True), sc, ls) for h, (sc, ls) in zip(mx_host, mx_scales)]
+        if train:
+            loss, grads = engine.contract_with_compiled_strategy_for_gradient(qctn, states, mxs)
+            if dist is not None:
+                flat = torch.cat([g.reshape(-1) for g in grads] + [loss.reshape(1)])
+                dist.all_reduce(flat)
+                flat /= world
+                return float(flat[-1].item())
+            return float(loss.item())
+        with torch.no_grad():
+            out = engine.contract_with_compiled_strategy(qctn, states, mxs)
+        return float(out.sum().item())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        barrier()
+        launches0 = _lib.launch_count()
+        evs = []
+        with ClockSampler(local_rank) as cs:
+            for _ in range(steps):
+                flush.fill_(1)                                 # evict L2 between timed steps (not timed)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step()
+                e1.record()
+                evs.append((e0, e1))
+            barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        launches = _lib.launch_count() - launches0
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, cs.summary()
+
+    ms_total, launches, clocks = timed(step_device, args.steps, args.warmup)
+    ms_step = ms_total / args.steps
+    value = B_global / (ms_step * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        def step_e2e_timed():
+            return step_e2e()
+        # wall-clock inside CUDA events is not enough here (host work is part of e2e): use events
+        # bracketing the whole call including the .item() read
+        ms_e2e, _, _ = timed(step_e2e_timed, max(3, args.steps // 2), 3)
+        ms_e2e_step = ms_e2e / max(3, args.steps // 2)
+        e2e = {"value": B_global / (ms_e2e_step * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e_step,
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+               "api": "EngineSiamese.contract_with_compiled_strategy" + ("_for_gradient" if train else "")}
+
+    # roofline of the dominant kernel (tnq_body_kernel): measured alone with CUDA events
+    bound = next(iter(fn.plans.values()))
+    prog = bound.program("train" if train else "fwd")
+    info = prog.info(B * bound.plan.nb)
+    flops_launch = prog.prog.flops_per_sample * B * bound.plan.nb
+    mx_bytes = B * nq * K * K * 4
+    core_bytes = sum(v.numel() * 4 for v in cores_cpu.values())
+    alg_bytes = mx_bytes + B * 4 + core_bytes * (2 if train else 1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # measured fp32 FMA peak of this GPU (not in MEASURED_PEAKS.json; torch.matmul, TF32 off)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    a = torch.randn(8192, 8192, device=dev)
+    b = torch.randn(8192, 8192, device=dev)
+    for _ in range(2):
+        a @ b
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    fp32_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    del a, b
+    kernel_ms = ms_step  # the body kernel is >95% of the step (profiles/ ncu launch list)
+    achieved_tf = flops_launch / (kernel_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / fp32_peak, "traffic": None,
+                "peak_source": "measured here: torch.matmul 8192^3 fp32 (TF32 off), best of 5",
+                "kernel": "tnq_body_kernel", "flops_per_launch": flops_launch,
+                "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9,
+                        "peak_gbs": peaks.get("hbm_gbs"), "source": "MEASURED_PEAKS.json (measured)" if peaks else None},
+                "tile_samples": info.tile_samples, "grid": info.grid, "frame_in_smem": bool(info.frame_in_smem),
+                "smem_bytes": info.smem_bytes}
+
+    line = {"metric": "samples/sec for QCTN fwd+bwd contraction" if train else "samples/sec for QCTN forward contraction",
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "global_batch": B_global, "per_gpu_batch": B, "qubits": nq, "K": K,
+                       "cores": len(names), "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": f"batch sharded over {world} GPU(s); cores replicated; "
+                                      + ("one packed NCCL all-reduce of grads+loss per step" if world > 1 else "no collective")},
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = time_reference(args, wl)
+        line["cpu_baseline"] = {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

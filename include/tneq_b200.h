@@ -1,0 +1,92 @@
+/*
+ * tneq_b200 C ABI  --  libtneq_b200.so
+ *
+ * Drop-in boundary for ONE path of the reference (tneq_qc): contracting a QCTN
+ * against a batch of measurement matrices (probabilities / loss / core
+ * gradients).  The reference has no FFI for this path: its boundary is the two
+ * Python plug-in registries BackendFactory.register_backend
+ * (tneq_qc/backends/backend_factory.py:91-100) and
+ * StrategyCompiler.register_strategy (tneq_qc/contractor/compiler.py:38-54).
+ * The Python host code in this repository implements those two interfaces and
+ * calls the functions below through ctypes; every entry point names the
+ * reference code it replaces.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - plain C types only; all device memory is owned by the caller (PyTorch);
+ *   - every function returns 0 on success, non-zero on error; the message is
+ *     available from tnq_last_error() (thread local);
+ *   - all work is enqueued on the CUDA stream passed in (a cudaStream_t cast to
+ *     void*); no hidden synchronisation; a plan is used by one host thread at a
+ *     time and belongs to the CUDA device that was current at creation;
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef TNEQ_B200_H
+#define TNEQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNQ_MAX_INPUTS 192
+#define TNQ_MAX_OUTPUTS 128
+
+typedef struct tnq_plan tnq_plan_t;
+
+/* Launch geometry chosen for a plan at a given batch (reported for bench/roofline). */
+typedef struct tnq_run_info {
+    int32_t tile_samples;     /* samples per tile (S) */
+    int32_t grid;             /* CTAs of the BODY kernel */
+    int32_t frame_in_smem;    /* 1: per-tile working set lives in shared memory */
+    int32_t launches;         /* kernels launched by one tnq_plan_run */
+    int64_t smem_bytes;       /* dynamic shared memory per CTA */
+    int64_t workspace_bytes;  /* scratch the caller must provide */
+} tnq_run_info_t;
+
+/* Library / device sanity: 0 when a CUDA device of compute capability 10.x is current. */
+int tnq_device_check(void);
+
+/*
+ * A plan is one compiled contraction program: the complete qubit sweep of
+ * GreedyStrategy.compute_fn (tneq_qc/contractor/greedy_strategy.py:45-598)
+ * -- optionally followed by the fused loss of
+ * EngineSiamese.contract_with_compiled_strategy_for_gradient
+ * (tneq_qc/core/engine_siamese.py:441-530) and the reverse sweep that
+ * torch.autograd.grad performs in BackendPyTorch.compute_value_and_grad
+ * (tneq_qc/backends/backend_pytorch.py:107-166).
+ * `blob` is the int64 encoding produced by contractor/vm_program.py.
+ */
+int tnq_plan_create(const int64_t* blob, int64_t nwords, tnq_plan_t** out);
+void tnq_plan_destroy(tnq_plan_t* plan);
+
+int tnq_plan_num_inputs(const tnq_plan_t* plan);
+int tnq_plan_num_outputs(const tnq_plan_t* plan);
+int tnq_plan_query(const tnq_plan_t* plan, int64_t nsamples, tnq_run_info_t* info);
+
+/*
+ * Run the plan on `nsamples` samples (= batch size x 2 when measurements are
+ * stacked (B,2,K,K), engine_siamese.py:683-719).
+ *   in_ptrs[i]        device pointer of input slot i (cores, circuit states,
+ *                     per-qubit measurement matrices, optional grad seed);
+ *   in_stride_hi/lo   for batched inputs: element offset of sample s is
+ *                     (s / nb) * hi + (s % nb) * lo  (nb is stored in the plan);
+ *   out_ptrs[j]       device pointer of output slot j (batched outputs are
+ *                     [nsamples, elems] row-major; shared ones [elems]);
+ *   scalars           host array {log_scale, 1/count}: the summed TNTensor
+ *                     log-scale and the mean weight of the fused loss;
+ *   workspace         device scratch of at least tnq_plan_query().workspace_bytes.
+ */
+int tnq_plan_run(tnq_plan_t* plan, int64_t nsamples, const void* const* in_ptrs,
+                 const int64_t* in_stride_hi, const int64_t* in_stride_lo, void* const* out_ptrs,
+                 const double* scalars, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t tnq_launch_count(void);
+
+const char* tnq_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNEQ_B200_H */

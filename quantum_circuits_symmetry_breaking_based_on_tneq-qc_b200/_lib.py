@@ -1,0 +1,58 @@
+"""ctypes binding of libtneq_b200.so (include/tneq_b200.h).
+
+The product has no CPU path: if the library is missing, or no B200 is
+visible, everything that would compute raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtneq_b200.so")
+
+EXPORTS = ["tnq_device_check", "tnq_plan_create", "tnq_plan_destroy", "tnq_plan_num_inputs",
+           "tnq_plan_num_outputs", "tnq_plan_query", "tnq_plan_run", "tnq_launch_count", "tnq_last_error"]
+
+
+class RunInfo(ctypes.Structure):
+    _fields_ = [("tile_samples", c_int32), ("grid", c_int32), ("frame_in_smem", c_int32), ("launches", c_int32),
+                ("smem_bytes", c_int64), ("workspace_bytes", c_int64)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  tneq_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.tnq_last_error.restype = c_char_p
+    lib.tnq_launch_count.restype = c_int64
+    lib.tnq_device_check.restype = c_int
+    lib.tnq_plan_create.argtypes = [POINTER(c_int64), c_int64, POINTER(c_void_p)]
+    lib.tnq_plan_destroy.argtypes = [c_void_p]
+    lib.tnq_plan_destroy.restype = None
+    lib.tnq_plan_num_inputs.argtypes = [c_void_p]
+    lib.tnq_plan_num_outputs.argtypes = [c_void_p]
+    lib.tnq_plan_query.argtypes = [c_void_p, c_int64, POINTER(RunInfo)]
+    lib.tnq_plan_run.argtypes = [c_void_p, c_int64, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64),
+                                 POINTER(c_void_p), POINTER(c_double), c_void_p, c_int64, c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError("tneq_b200: " + load().tnq_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(load().tnq_launch_count())

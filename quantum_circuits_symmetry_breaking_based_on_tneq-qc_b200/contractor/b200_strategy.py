@@ -1,0 +1,291 @@
+"""B200Strategy: the contraction strategy whose compute function runs the whole
+qubit sweep as hand-written sm_100a CUDA (libtneq_b200.so).
+
+Plug-in contract (reference: tneq_qc/contractor/base.py:12-62, used by
+tneq_qc/contractor/compiler.py:66-126 and tneq_qc/core/engine_siamese.py:261-554):
+
+    strategy.get_compute_function(qctn, shapes_info, backend, right_qctn="symmetric")
+        -> compute_fn(cores_dict, circuit_states, measure_matrices, right_cores_dict=None)
+
+compute_fn has the semantics of GreedyStrategy.compute_fn
+(tneq_qc/contractor/greedy_strategy.py:45-598):
+  * cores / states / measurements may be torch tensors or TNTensors; if any
+    operand is a TNTensor the result is TNTensor(raw, scale=prod scales,
+    log_scale=sum log_scales) (greedy_strategy.py:913-952), the host floats being
+    combined in exactly the reference's operand order;
+  * measurements are (B,K,K) or (B,2,K,K); None leaves that qubit's edges open;
+  * the result is differentiable w.r.t. the core tensors (torch.autograd);
+  * errors are Python exceptions (ValueError / RuntimeError).
+Extra, used by this repository's own engine: compute_fn.loss_and_grads(...) runs
+forward + loss + reverse sweep as one fused device program.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from ..core.tn_tensor import TNTensor
+from .base import ContractionStrategy
+from .device_plan import DeviceProgram
+from .plan import ContractionPlan, signature_of
+
+_DTYPE_NAME = {torch.float32: "float32", torch.float64: "float64",
+               torch.complex64: "complex64", torch.complex128: "complex128"}
+
+
+def _is_tnt(x) -> bool:
+    return hasattr(x, "tensor") and hasattr(x, "scale") and hasattr(x, "log_scale")
+
+
+def _raw(x):
+    return x.tensor if _is_tnt(x) else x
+
+
+def _items(container, n):
+    """qubit -> entry for the containers the reference accepts (None, dict, list, tuple)."""
+    if container is None:
+        return {}
+    if isinstance(container, dict):
+        return {q: container[q] for q in range(n) if q in container}
+    return {q: container[q] for q in range(min(n, len(container)))}
+
+
+def _real_view(t: torch.Tensor) -> torch.Tensor:
+    return torch.view_as_real(t) if t.is_complex() else t
+
+
+class _Bound:
+    """One plan bound to one device: lowered programs are created lazily."""
+
+    def __init__(self, plan: ContractionPlan, device: torch.device):
+        self.plan, self.device = plan, device
+        self._dev: Dict[str, DeviceProgram] = {}
+
+    def program(self, mode: str) -> DeviceProgram:
+        if mode not in self._dev:
+            self._dev[mode] = DeviceProgram(self.plan.program(mode), self.device)
+        return self._dev[mode]
+
+
+class _SweepFn(torch.autograd.Function):
+    """forward: 'fwd' program; backward: 'bwd' program (forward recomputation + reverse sweep
+    in one launch, nothing but the inputs is kept alive between the two)."""
+
+    @staticmethod
+    def forward(ctx, call, *cores):
+        ctx.call = call
+        ctx.save_for_backward(*cores)
+        return call.forward(cores)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grads = ctx.call.backward(ctx.saved_tensors, grad_out)
+        return (None,) + tuple(g if need else None for g, need in zip(grads, ctx.needs_input_grad[1:]))
+
+
+class _Call:
+    """Everything about one invocation except the core tensors."""
+
+    def __init__(self, bound: _Bound, core_keys, states, mxs, B, dtype):
+        self.bound, self.core_keys, self.states, self.mxs, self.B, self.dtype = bound, core_keys, states, mxs, B, dtype
+        self.nb = bound.plan.nb
+        self.nsamples = B * self.nb
+
+    def _inputs(self, prog: DeviceProgram, cores, seed=None):
+        out = []
+        by_key = dict(zip(self.core_keys, cores))
+        for slot in prog.prog.inputs:
+            kind, key = slot.key
+            if kind in ("core", "rcore"):
+                t = _real_view(by_key[(kind, key)].detach().contiguous())
+                out.append((t, 0, 0))
+            elif kind == "state":
+                out.append((_real_view(self.states[key].detach().contiguous()), 0, 0))
+            elif kind == "mx":
+                m = self.mxs[key].detach()
+                inner = m.shape[-2] * m.shape[-1]
+                if m.stride(-1) != 1 or m.stride(-2) != m.shape[-1]:
+                    m = m.contiguous()
+                mul = 2 if m.is_complex() else 1
+                if m.dim() == 4:
+                    hi, lo = m.stride(0) * mul, m.stride(1) * mul
+                else:
+                    hi, lo = m.stride(0) * mul, 0
+                if m.shape[0] == 1 and self.B != 1:
+                    hi = 0
+                out.append((_real_view(m), hi, lo))
+                assert slot.elems == inner * mul
+            elif kind == "gradseed":
+                out.append((seed, slot.elems * self.nb, slot.elems))
+            else:
+                raise RuntimeError(f"unknown input slot {slot.key}")
+        return out
+
+    def _shape_result(self, flat: torch.Tensor) -> torch.Tensor:
+        g = self.bound.plan.graph("fwd")
+        res = g.nodes[g.result]
+        body = [g.dims[i] for i in (res.idx[:-1] if res.cplx else res.idx)]
+        lead = [self.B] + ([2] if self.nb == 2 else [])
+        if res.cplx:
+            return torch.view_as_complex(flat.reshape(lead + body + [2]))
+        return flat.reshape(lead + body)
+
+    def forward(self, cores):
+        prog = self.bound.program("fwd")
+        (flat,) = prog.run(self.nsamples, self._inputs(prog, cores))
+        return self._shape_result(flat)
+
+    def backward(self, cores, grad_out):
+        prog = self.bound.program("bwd")
+        seed = _real_view(grad_out.contiguous()).reshape(self.nsamples, -1).to(prog.real_dtype).contiguous()
+        outs = prog.run(self.nsamples, self._inputs(prog, cores, seed=seed))
+        return self._grads(prog, outs, cores)
+
+    def _grads(self, prog, outs, cores):
+        grads = []
+        for key, c in zip(self.core_keys, cores):
+            gflat = outs[prog.prog.output_index(("grad",) + key)]
+            if c.is_complex():
+                grads.append(torch.view_as_complex(gflat.reshape(tuple(c.shape) + (2,))))
+            else:
+                grads.append(gflat.reshape(c.shape))
+        return grads
+
+    def train(self, cores, log_scale: float):
+        """Fused forward + loss + reverse sweep.  Returns (loss, grads, values)."""
+        prog = self.bound.program("train")
+        outs = prog.run(self.nsamples, self._inputs(prog, cores), scalars=(log_scale, 1.0 / self.nsamples))
+        loss = outs[prog.prog.output_index(("loss", 0))][0]
+        values = self._shape_result(outs[prog.prog.output_index(("result", 0))])
+        return loss, self._grads(prog, outs, cores), values
+
+
+class B200Strategy(ContractionStrategy):
+    """Whole-sweep CUDA contraction; registered for modes 'balanced' and 'full'."""
+
+    def check_compatibility(self, qctn, shapes_info: Dict[str, Any]) -> bool:
+        return True
+
+    def estimate_cost(self, qctn, shapes_info: Dict[str, Any]) -> float:
+        # below GreedyStrategy's fixed 5e5 (greedy_strategy.py:602-608) so that
+        # StrategyCompiler.compile (compiler.py:123) picks this strategy
+        return 1e5
+
+    @property
+    def name(self) -> str:
+        return "b200"
+
+    def get_compute_function(self, qctn, shapes_info: Dict[str, Any], backend, right_qctn="symmetric") -> Callable:
+        plans: Dict[Any, _Bound] = {}
+        nq = qctn.nqubits
+        table = qctn.adjacency_table
+        core_names = list(qctn.cores)
+        if right_qctn is None or (isinstance(right_qctn, str) and right_qctn == "symmetric"):
+            right_mode, right_table, right_names = right_qctn, None, []
+        elif hasattr(right_qctn, "adjacency_table"):
+            right_mode, right_table, right_names = "qctn", right_qctn.adjacency_table, list(right_qctn.cores)
+        else:
+            raise ValueError("Invalid right_qctn parameter.")
+
+        def prepare(cores_dict, circuit_states, measure_matrices, right_cores_dict):
+            """-> (call, raw core tensors, per-operand scale bookkeeping)"""
+            cores_w = {k: cores_dict[k] for k in core_names}
+            rcores_w = {k: right_cores_dict[k] for k in right_names} if right_mode == "qctn" else {}
+            states_w, mxs_w = _items(circuit_states, nq), _items(measure_matrices, nq)
+            mxs_w = {q: m for q, m in mxs_w.items() if m is not None}
+            tensors = [_raw(v) for v in list(cores_w.values()) + list(rcores_w.values())]
+            if not tensors:
+                raise RuntimeError("No tensor left after contraction")
+            dtype = tensors[0].dtype
+            for t in [_raw(v) for v in list(states_w.values()) + list(mxs_w.values())] + tensors[1:]:
+                dtype = torch.promote_types(dtype, t.dtype)
+            if dtype not in _DTYPE_NAME:
+                raise ValueError(f"unsupported dtype {dtype}")
+            device = tensors[0].device
+            if device.type != "cuda":
+                raise RuntimeError("B200Strategy needs CUDA tensors: tneq_b200 has no CPU fallback")
+
+            def conv(t):
+                t = _raw(t)
+                if t.device != device or t.dtype != dtype:
+                    t = t.to(device=device, dtype=dtype)
+                return t
+
+            states = {q: conv(s) for q, s in states_w.items()}
+            mxs = {q: conv(m) for q, m in mxs_w.items()}
+            for q, s in states.items():
+                if s.dim() != 1:
+                    raise ValueError(f"circuit state of qubit {q} must be 1-D (got shape {tuple(s.shape)}); "
+                                     "batched circuit states are not supported by the greedy contraction")
+            B = None
+            for q, m in mxs.items():
+                if m.dim() not in (3, 4) or (m.dim() == 4 and m.shape[1] != 2):
+                    raise ValueError(f"measurement of qubit {q} must be (B,K,K) or (B,2,K,K), got {tuple(m.shape)}")
+                if m.shape[0] != 1:
+                    if B is not None and B != m.shape[0]:
+                        raise ValueError("measurement matrices disagree on the batch size")
+                    B = m.shape[0]
+            if B is None:
+                B = 1
+            state_dims, mx_info = signature_of(nq, states_w, {q: mxs_w.get(q) for q in range(nq)})
+            key = (tuple(sorted(state_dims.items())), tuple(sorted(mx_info.items())), dtype, str(device))
+            if key not in plans:
+                shapes = {k: tuple(_raw(v).shape) for k, v in cores_w.items()}
+                rshapes = {k: tuple(_raw(v).shape) for k, v in rcores_w.items()}
+                plan = ContractionPlan(table, nq, shapes, state_dims, mx_info, _DTYPE_NAME[dtype], right=right_mode,
+                                       right_table=right_table, right_core_shapes=rshapes)
+                plans[key] = _Bound(plan, device)
+            bound = plans[key]
+            core_keys = [("core", k) for k in core_names] + [("rcore", k) for k in right_names]
+            cores = [conv(v) for v in list(cores_w.values()) + list(rcores_w.values())]
+            call = _Call(bound, core_keys, states, mxs, B, dtype)
+            # TNTensor scale of the result, combined in the reference's order
+            # (greedy_strategy.py:913-933): per step, left to right over its operands
+            wrapped = {("core", k): v for k, v in cores_w.items()}
+            wrapped.update({("rcore", k): v for k, v in rcores_w.items()})
+            wrapped.update({("state", q): v for q, v in states_w.items()})
+            wrapped.update({("mx", q): v for q, v in mxs_w.items()})
+            tmp: Dict[int, Optional[Tuple[float, float]]] = {}
+            for step in bound.plan.schedule.steps:
+                sc = ls = None
+                for op in step.operands:
+                    if op.kind == "tmp":
+                        pair = tmp[op.key]
+                    else:
+                        w = wrapped[("core", op.key) if op.kind == "core_conj" else (op.kind, op.key)]
+                        pair = (w.scale, w.log_scale) if _is_tnt(w) else None
+                    if pair is not None:
+                        sc = pair[0] if sc is None else sc * pair[0]
+                        ls = pair[1] if ls is None else ls + pair[1]
+                tmp[step.out] = None if sc is None else (sc, ls)
+            return call, cores, tmp[bound.plan.schedule.result.key]
+
+        def compute_fn(cores_dict, circuit_states, measure_matrices, right_cores_dict=None):
+            call, cores, scale = prepare(cores_dict, circuit_states, measure_matrices, right_cores_dict)
+            if torch.is_grad_enabled() and any(c.requires_grad for c in cores):
+                res = _SweepFn.apply(call, *cores)
+            else:
+                res = call.forward(cores)
+            if scale is not None:
+                return TNTensor(res, scale=scale[0], log_scale=scale[1])
+            return res
+
+        def loss_and_grads(cores_dict, circuit_states, measure_matrices, right_cores_dict=None):
+            """Fused -mean(log(clamp(value,1e-10)) + log_scale) and its core gradients
+            (engine_siamese.py:441-554), one device program."""
+            call, cores, scale = prepare(cores_dict, circuit_states, measure_matrices, right_cores_dict)
+            loss, grads, values = call.train(cores, 0.0 if scale is None else float(scale[1]))
+            return loss, grads, values, scale
+
+        def equations(circuit_states, measure_matrices):
+            """The per-qubit einsum strings of this signature (index bookkeeping parity)."""
+            sd, mi = signature_of(nq, circuit_states, measure_matrices)
+            from .greedy_plan import build_schedule
+            return build_schedule(table, nq, sd, mi, right=right_mode, right_table=right_table).equations
+
+        compute_fn.loss_and_grads = loss_and_grads
+        compute_fn.equations = equations
+        compute_fn.plans = plans
+        return compute_fn

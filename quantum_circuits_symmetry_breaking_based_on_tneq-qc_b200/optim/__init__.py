@@ -1,0 +1,3 @@
+from .optimizer import Optimizer
+
+__all__ = ["Optimizer"]

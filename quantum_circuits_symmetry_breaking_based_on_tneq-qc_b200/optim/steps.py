@@ -1,0 +1,144 @@
+"""Parameter updates (reference: tneq_qc/backends/backend_pytorch.py:200-468).
+
+optimizer_update(params, grads, state, method, hyperparams) -> (new_params, state)
+with methods adam | sgd | momentum | nesterov | rmsprop | sgdg.  'sgdg' is the
+Stiefel-manifold SGD with a Cayley retraction used by the examples
+(examples/example_train_single_node.py:229-240).  Params may be TNTensors:
+the update acts on tensor*scale with grad/scale and re-wraps (:205-266).
+
+These are small dense per-core operations (K^2 x K^2 matrices); they run on the
+device through torch for now -- SURVEY 8(f) item 1 lists a batched CUDA kernel
+for them as the next step after the contraction path.
+"""
+from __future__ import annotations
+
+import random
+from typing import Any, Dict, List, Tuple
+
+import numpy as np
+import torch
+
+
+def _is_tnt(p):
+    return hasattr(p, "tensor") and hasattr(p, "scale") and hasattr(p, "auto_scale")
+
+
+def optimizer_update(params: List[Any], grads: List[Any], state: Dict[str, Any], method: str,
+                     hp: Dict[str, Any]) -> Tuple[List[Any], Dict[str, Any]]:
+    fn = {"adam": _adam, "sgd": _sgd, "momentum": _momentum, "nesterov": _nesterov,
+          "rmsprop": _rmsprop, "sgdg": _sgdg}.get(method)
+    if fn is None:
+        raise ValueError(f"Unknown optimization method: {method}")
+    with torch.no_grad():
+        raw, info = [], []
+        for p in params:
+            if _is_tnt(p):
+                raw.append(p.tensor * p.scale)
+                info.append((p.scale, type(p)))
+            else:
+                raw.append(p)
+                info.append(None)
+        g = [gi / inf[0] if inf is not None else gi for gi, inf in zip(grads, info)]
+        new, state = fn(raw, g, state, hp)
+        for i, inf in enumerate(info):
+            if inf is not None:
+                params[i] = inf[1](new[i] / inf[0], inf[0])
+                params[i].tensor.requires_grad_(True)
+            else:
+                params[i] = new[i]
+                params[i].requires_grad_(True)
+    return params, state
+
+
+def _adam(params, grads, state, hp):
+    lr, b1, b2 = hp.get("learning_rate", 0.01), hp.get("beta1", 0.9), hp.get("beta2", 0.999)
+    eps, it = hp.get("epsilon", 1e-8), hp.get("iter", 0)
+    if "m" not in state:
+        state["m"] = [torch.zeros_like(p) for p in params]
+        state["v"] = [torch.zeros_like(p) for p in params]
+    out = []
+    for i, (p, g) in enumerate(zip(params, grads)):
+        state["m"][i] = b1 * state["m"][i] + (1 - b1) * g
+        state["v"][i] = b2 * state["v"][i] + (1 - b2) * (g ** 2)
+        mh = state["m"][i] / (1 - b1 ** (it + 1))
+        vh = state["v"][i] / (1 - b2 ** (it + 1))
+        out.append(p - lr * mh / (torch.sqrt(vh) + eps))
+    return out, state
+
+
+def _sgd(params, grads, state, hp):
+    lr = hp.get("learning_rate", 0.01)
+    return [p - lr * g for p, g in zip(params, grads)], state
+
+
+def _momentum(params, grads, state, hp):
+    lr = hp.get("learning_rate", 0.01)
+    if "momentum_buffer" not in state:
+        state["momentum_buffer"] = [torch.zeros_like(p) for p in params]
+    out = []
+    for i, (p, g) in enumerate(zip(params, grads)):
+        state["momentum_buffer"][i] = 0.9 * state["momentum_buffer"][i] + lr * g
+        out.append(p - state["momentum_buffer"][i])
+    return out, state
+
+
+def _nesterov(params, grads, state, hp):
+    lr = hp.get("learning_rate", 0.01)
+    if "momentum_buffer" not in state:
+        state["momentum_buffer"] = [torch.zeros_like(p) for p in params]
+    out = []
+    for i, (p, g) in enumerate(zip(params, grads)):
+        state["momentum_buffer"][i] = 0.9 * state["momentum_buffer"][i] + lr * g
+        out.append(p - (state["momentum_buffer"][i] + lr * g))
+    return out, state
+
+
+def _rmsprop(params, grads, state, hp):
+    lr, eps = hp.get("learning_rate", 0.01), hp.get("epsilon", 1e-8)
+    if "square_avg" not in state:
+        state["square_avg"] = [torch.zeros_like(p) for p in params]
+    out = []
+    for i, (p, g) in enumerate(zip(params, grads)):
+        state["square_avg"][i] = 0.9 * state["square_avg"][i] + 0.1 * (g ** 2)
+        out.append(p - lr * g / (torch.sqrt(state["square_avg"][i]) + eps))
+    return out, state
+
+
+def _sgdg(params, grads, state, hp):
+    """Cayley-transform SGD on the Stiefel manifold (backend_pytorch.py:349-468)."""
+    lr, mom, stiefel = hp.get("learning_rate", 0.01), hp.get("momentum", 0.0), hp.get("stiefel", True)
+    eps = 1e-8
+    if "momentum_buffer" not in state:
+        state["momentum_buffer"] = [None] * len(params)
+    out = []
+    for i, (p, g) in enumerate(zip(params, grads)):
+        shp = p.shape
+        if len(shp) > 2:
+            rows = int(np.prod(shp[: len(shp) // 2]))
+            x, gx = p.reshape(rows, -1), g.reshape(rows, -1)
+        else:
+            x, gx = p, g
+        cplx = torch.is_complex(x)
+        unity = x / (torch.norm(x, p=2, dim=1, keepdim=True) + eps)
+        if not (stiefel and unity.shape[0] <= unity.shape[1]):
+            out.append(p - lr * g)
+            continue
+        if random.randint(1, 101) == 1:  # occasional QR retraction, same RNG stream as the reference
+            qm, rm = torch.linalg.qr(unity.T, mode="reduced")
+            d = torch.diag(rm)
+            unity = (qm * (torch.sgn(d) if torch.is_complex(d) else torch.sign(d)).unsqueeze(0)).T
+        if state["momentum_buffer"][i] is None:
+            state["momentum_buffer"][i] = torch.zeros(gx.T.shape, dtype=gx.dtype, device=p.device)
+        hconj = (lambda m: torch.conj(m).T) if cplx else (lambda m: m.T)
+        v = mom * state["momentum_buffer"][i] - hconj(gx)
+        mx = v @ unity
+        w_hat = mx - 0.5 * (hconj(unity) @ (unity @ mx))
+        w = w_hat - hconj(w_hat)
+        t = 0.5 * 2 / (torch.abs(w).sum(dim=0).max() + eps)
+        alpha = min(t, lr)
+        eye = torch.eye(w.shape[0], dtype=w.dtype, device=w.device)
+        y = torch.inverse(eye - (alpha / 2) * w) @ (eye + (alpha / 2) * w) @ hconj(unity)
+        pn = hconj(y)
+        out.append(pn.reshape(shp) if len(shp) > 2 else pn)
+        state["momentum_buffer"][i] = w @ hconj(unity)
+    return out, state

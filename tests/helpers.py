@@ -1,0 +1,73 @@
+"""Shared helpers for the tests (oracle-side data + comparisons)."""
+import numpy as np
+import torch
+
+from oracle import qctn_oracle as oc
+
+
+def make_case(graph, K, B, dtype, tnt=True, mode="a", seed=0, identity_q=()):
+    """Seeded CPU inputs for one contraction: cores, unit states, measurement matrices."""
+    torch.manual_seed(seed)
+    td = getattr(torch, dtype)
+    names, table, nq = oc.parse_graph(graph)
+    cores = oc.random_cores(table, td)
+    x = torch.randn(B, nq)
+    mxs, _ = oc.generate_data(x, K, td, "TNTensor" if tnt else "tensor")
+    if identity_q:
+        eye = torch.eye(K, dtype=td).expand(B, K, K)
+        mxs = [eye if q in identity_q else m for q, m in enumerate(mxs)]
+    if mode == "ab":
+        eye = torch.eye(K, dtype=td).expand(B, K, K)
+        mxs = [torch.stack([oc._raw(m), eye], dim=1) for m in mxs]
+    states = oc.unit_states(nq, K, td)
+    return names, table, nq, cores, states, mxs
+
+
+def clone_mx(mxs):
+    out = []
+    for m in mxs:
+        if isinstance(m, oc.TNT):
+            out.append(oc.TNT(m.tensor.clone(), m.scale, m.log_scale))
+        else:
+            out.append(m.clone())
+    return out
+
+
+def rel_err(got, want):
+    got, want = torch.as_tensor(got).detach().cpu(), torch.as_tensor(want).detach().cpu()
+    return ((got - want).abs().max() / want.abs().max().clamp_min(1e-300)).item()
+
+
+def elem_rel_err(got, want, floor=0.0):
+    got, want = torch.as_tensor(got).detach().cpu(), torch.as_tensor(want).detach().cpu()
+    return ((got - want).abs() / want.abs().clamp_min(floor if floor > 0 else 1e-300)).max().item()
+
+
+def well_conditioned_case(graph, K, B, dtype, seed=0, keep=0.05, mode="a"):
+    """Like make_case, but only keeps samples whose float64 value is at least `keep` x the
+    median.  Samples whose amplitude almost cancels lose every digit in float32 in ANY
+    implementation (the reference included) and, because d log p = dp / p, they dominate the
+    gradient error; parity to 1e-5 is only meaningful away from them ("Parity")."""
+    torch.manual_seed(seed)
+    td = getattr(torch, dtype)
+    td64 = torch.complex128 if td.is_complex else torch.float64
+    names, table, nq = oc.parse_graph(graph)
+    cores = oc.random_cores(table, td)
+    states = oc.unit_states(nq, K, td)
+    x = torch.randn(6 * B, nq)
+    mx64, _ = oc.generate_data(x, K, td64, "tensor")
+    p = oc.forward(graph, {k: v.to(td64) for k, v in cores.items()}, [s.to(td64) for s in states], mx64)
+    order = torch.argsort(p, descending=True)
+    good = order[p[order] >= keep * p.median()][:B]
+    assert len(good) == B, "not enough well-conditioned samples"
+    mxs, _ = oc.generate_data(x[good], K, td, "TNTensor")
+    if mode == "ab":
+        eye = torch.eye(K, dtype=td).expand(B, K, K)
+        mxs = [torch.stack([oc._raw(m), eye], dim=1) for m in mxs]
+    return names, table, nq, cores, states, mxs
+
+
+def upcast(x, td):
+    if isinstance(x, oc.TNT):
+        return oc.TNT(x.tensor.to(td), x.scale, x.log_scale)
+    return x.to(td)

@@ -1,0 +1,172 @@
+"""GPU parity: the CUDA path (through the engine API and the C ABI) against the oracle.
+
+Tolerance (BASELINE.json north_star): probabilities and gradients within 1e-5
+relative for float32 / complex64.  "Relative" is measured per tensor against its
+largest magnitude for gradients (elements near zero carry no relative
+information in float32) and per sample for probabilities; both sides compute in
+float32 with different summation orders, so the oracle in float64 is used as
+the common yardstick where stated.
+"""
+import pytest
+import torch
+
+import tneq_b200
+from oracle import qctn_oracle as oc
+from helpers import make_case, well_conditioned_case, upcast, clone_mx, rel_err, elem_rel_err
+
+pytestmark = pytest.mark.gpu
+
+H = tneq_b200.QCTNHelper
+
+
+def _graph(kind, n, K):
+    if kind == "merged":
+        q = tneq_b200.QCTN(H.generate_example_graph(n=n, graph_type="mps", dim_char=str(K)))
+        return tneq_b200.QCTN.merge(q, q).graph
+    return H.generate_example_graph(n=n, graph_type=kind, dim_char=str(K))
+
+
+def _to_dev(x, dev):
+    if isinstance(x, oc.TNT):
+        return tneq_b200.TNTensor(x.tensor.to(dev), x.scale, x.log_scale)
+    return x.to(dev)
+
+
+def _engine(dtype, K, built_lib):
+    be = tneq_b200.BackendFactory.create_backend("b200", device="cuda:0", dtype=dtype)
+    return be, tneq_b200.EngineSiamese(backend=be, strategy_mode="balanced", mx_K=K)
+
+
+CASES = [
+    ("mps", 6, 3, 37, "float32", "a"),
+    ("mps", 16, 3, 300, "float32", "a"),
+    ("mps", 5, 2, 33, "float64", "a"),
+    ("mps", 6, 3, 19, "complex64", "a"),
+    ("mps", 5, 2, 8, "complex128", "a"),
+    ("tree", 6, 2, 65, "float32", "a"),
+    ("tree", 7, 3, 21, "float32", "a"),
+    ("wall", 4, 2, 16, "float32", "a"),
+    ("merged", 4, 2, 50, "float32", "a"),
+    ("merged", 6, 3, 40, "float32", "a"),
+    ("merged", 4, 2, 9, "complex64", "a"),
+    ("mps", 6, 3, 10, "float32", "ab"),
+    ("mps", 4, 4, 130, "float32", "a"),
+]
+
+
+@pytest.mark.parametrize("kind,n,K,B,dtype,mode", CASES)
+def test_forward_and_training_step(kind, n, K, B, dtype, mode, built_lib):
+    """Probabilities, loss and core gradients of the CUDA path vs the oracle on the same inputs.
+    Tolerance 1e-5 relative (north_star) for float32/complex64, measured per tensor against its
+    largest entry, on well-conditioned samples (see helpers.well_conditioned_case); 1e-11 for
+    float64/complex128.  The float64 oracle on the same float32 inputs is the common yardstick:
+    the CUDA path must be as close to it as the reference's own float32 arithmetic is."""
+    graph = _graph(kind, n, K)
+    names, table, nq, cores, states, mxs = well_conditioned_case(graph, K, B, dtype, mode=mode)
+    single = dtype in ("float32", "complex64")
+    tol = 1e-5 if single else 1e-11
+    td64 = torch.complex128 if "complex" in dtype else torch.float64
+    want = oc.forward(graph, cores, states, clone_mx(mxs))
+    c64 = {k: v.to(td64) for k, v in cores.items()}
+    s64 = [s.to(td64) for s in states]
+    truth = oc.forward(graph, c64, s64, [upcast(m, td64) for m in clone_mx(mxs)])
+    be, eng = _engine(dtype, K, built_lib)
+    dev = torch.device("cuda:0")
+    q = tneq_b200.QCTN(graph, backend=be)
+    for k, v in cores.items():
+        q.cores_weights[k] = v.to(dev).requires_grad_(True)
+    st = [s.to(dev) for s in states]
+    got = eng.contract_with_compiled_strategy(q, st, [_to_dev(m, dev) for m in clone_mx(mxs)])
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert rel_err(got, want) < tol
+    assert elem_rel_err(got.double(), truth) < max(tol, 3 * elem_rel_err(want.double(), truth))
+
+    if mode == "ab":
+        return
+    wl, wg = oc.loss_and_grads(graph, cores, states, clone_mx(mxs))
+    tl, tg = oc.loss_and_grads(graph, c64, s64, [upcast(m, td64) for m in clone_mx(mxs)])
+    for fused in (True, False):   # fused device program, then the torch.autograd route
+        loss, grads = eng.contract_with_compiled_strategy_for_gradient(
+            q, st, [_to_dev(m, dev) for m in clone_mx(mxs)], fused=fused)
+        assert abs(loss.item() - wl.item()) <= tol * abs(wl.item())
+        assert len(grads) == len(wg)
+        for g, w, t in zip(grads, wg, tg):
+            assert g.shape == w.shape and g.dtype == w.dtype
+            ref_err = rel_err(w.to(td64), t)
+            assert rel_err(g.to(td64), t) < max(tol, 3 * ref_err), (fused, rel_err(g.to(td64), t), ref_err)
+            assert rel_err(g, w) < max(tol, 4 * ref_err)
+
+
+def test_kat_normalisation_identity_measurements(built_lib):
+    """KAT-1: orthogonal cores + identity on every qubit => value == 1 for every sample."""
+    for kind, n, K in [("mps", 8, 3), ("merged", 4, 2), ("tree", 6, 2)]:
+        graph = _graph(kind, n, K)
+        names, table, nq, cores, states, mxs = make_case(graph, K, 5, "float32", tnt=False, identity_q=range(64))
+        be, eng = _engine("float32", K, built_lib)
+        q = tneq_b200.QCTN(graph, backend=be)
+        for k, v in cores.items():
+            q.cores_weights[k] = v.cuda()
+        got = eng.contract_with_compiled_strategy(q, [s.cuda() for s in states], [m.cuda() for m in mxs])
+        assert torch.allclose(got.cpu(), torch.ones(5), atol=2e-6)
+
+
+def test_kat_identity_circuit(built_lib):
+    """KAT-2: identity cores, states e_{K-1} => P_b = prod_q Mx_q[b, K-1, K-1]."""
+    K, n, B = 3, 6, 11
+    graph = _graph("mps", n, K)
+    names, table, nq, cores, states, mxs = make_case(graph, K, B, "float64", tnt=False)
+    be, eng = _engine("float64", K, built_lib)
+    q = tneq_b200.QCTN(graph, backend=be)
+    for k in q.cores:
+        q.cores_weights[k] = torch.eye(K * K, dtype=torch.float64).reshape(K, K, K, K).cuda()
+    got = eng.contract_with_compiled_strategy(q, [s.cuda() for s in states], [m.cuda() for m in mxs])
+    want = torch.ones(B, dtype=torch.float64)
+    for m in mxs:
+        want = want * m[:, K - 1, K - 1]
+    assert rel_err(got, want) < 1e-12
+
+
+def test_conditional_probability_identity(built_lib):
+    """The only numeric assertion of the reference's own test file
+    (tests/test_probabilities.py:84-87): P(t|c) == P(t,c) / P(c), atol 1e-5."""
+    K, n, B = 2, 4, 6
+    graph = _graph("mps", n, K)
+    names, table, nq, cores, states, mxs = make_case(graph, K, B, "float32", tnt=False)
+    be, eng = _engine("float32", K, built_lib)
+    q = tneq_b200.QCTN(graph, backend=be)
+    for k, v in cores.items():
+        q.cores_weights[k] = v.cuda()
+    st = [s.cuda() for s in states]
+    m = [x.cuda() for x in mxs]
+    joint = eng.calculate_marginal_probability(q, st, [m[0], m[1]], [0, 1])
+    marg = eng.calculate_marginal_probability(q, st, [m[0]], [0])
+    cond = eng.calculate_conditional_probability(q, st, [m[0], m[1]], [0, 1], [1])
+    assert torch.allclose(cond, joint / (marg + 1e-10), atol=1e-5)
+
+
+def test_sampling_shape_and_bounds(built_lib):
+    """tests/test_probabilities.py:296-333: shape (S, n) and -5 <= samples <= 5."""
+    K, n = 3, 4
+    graph = _graph("mps", n, K)
+    be, eng = _engine("float32", K, built_lib)
+    q = tneq_b200.QCTN(graph, backend=be)
+    st = [s.cuda() for s in oc.unit_states(n, K)]
+    samples = eng.sample(q, st, num_samples=50, K=K, bounds=[-5, 5], grid_size=40)
+    assert tuple(samples.shape) == (50, n)
+    assert (samples >= -5).all() and (samples <= 5).all()
+
+
+def test_large_batch_and_ragged_tail(built_lib):
+    """Batch sizes that are not a multiple of the tile, and one bigger than a wave."""
+    K, n = 3, 8
+    graph = _graph("mps", n, K)
+    for B in (1, 127, 20011):
+        names, table, nq, cores, states, mxs = make_case(graph, K, B, "float32", tnt=True, seed=B)
+        want = oc.forward(graph, cores, states, clone_mx(mxs))
+        be, eng = _engine("float32", K, built_lib)
+        q = tneq_b200.QCTN(graph, backend=be)
+        for k, v in cores.items():
+            q.cores_weights[k] = v.cuda()
+        got = eng.contract_with_compiled_strategy(q, [s.cuda() for s in states],
+                                                  [_to_dev(m, torch.device("cuda:0")) for m in clone_mx(mxs)])
+        assert rel_err(got, want) < 2e-5
