@@ -41,6 +41,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "cfg3": dict(kind="merged", n=24, K=3, batch=16384, mode="train", dtype="float32",
                  name="cfg3: 24-qubit 2-layer merged MPS QCTN, K=3, fwd+loss+bwd, global batch 16384"),
+    "cfg3-fwd": dict(kind="merged", n=24, K=3, batch=16384, mode="fwd", dtype="float32",
+                     name="24-qubit 2-layer merged MPS QCTN, K=3, forward only, batch 16384"),
     "cfg2": dict(kind="mps", n=16, K=3, batch=4096, mode="fwd", dtype="float32",
                  name="cfg2: 16-qubit MPS QCTN, K=3, forward probabilities, batch 4096"),
     "cfg2-large": dict(kind="mps", n=16, K=3, batch=1 << 20, mode="fwd", dtype="float32",

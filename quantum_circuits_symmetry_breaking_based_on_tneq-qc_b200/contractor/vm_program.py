@@ -24,6 +24,8 @@ Spaces: 0 CONST (pool of prepared shared tensors)   1 FRAME (per-sample scratch)
 Ops (24 int64 words each; T = tables are offsets into itab / ftab):
   LIN   dst[j] (=|+=) c0[j]*src[s0[j]] + c1[j]*src[s1[j]]           j < count
   GEMM  C[cm[r]+cn[c]] (=|+=) sum_k A[am[r]+ak[k]] * B[bk[k]+bn[c]]   r < nm, c < nn
+        (w[20] = TN column tile; w[22] = 1: B is a packed PREP copy [k][c/TN][TN padded to 16 B],
+         row length w[21], so bk[k] = k*ldb and a thread's TN columns are contiguous and aligned)
   RGEMM G[gk[i]+gn[c]] += sum_{samples in tile} sum_r A[am[r]+ak[i]] * D[dm[r]+dn[c]]
   SEED  fused loss: value -> d(loss)/d(value), loss partial  (engine_siamese.py:490-530)
 All tensors are compact row-major in their index order, so offsets are plain
@@ -143,6 +145,14 @@ def _offsets(g: CGraph, order, strides):
     return off
 
 
+def _pick_tile(extent: int, choices) -> int:
+    """Largest register-tile edge from `choices` that divides `extent`."""
+    for c in choices:
+        if extent % c == 0:
+            return c
+    return 1
+
+
 def lower(g: CGraph, mode: str, dtype: str, nb: int = 1, emit_values: bool = True) -> VMProgram:
     """mode: 'fwd'   result only
              'bwd'   forward recomputation + reverse sweep seeded by the caller's grad (autograd route)
@@ -231,6 +241,7 @@ def lower(g: CGraph, mode: str, dtype: str, nb: int = 1, emit_values: bool = Tru
 
     prep_ops: List[dict] = []
     fin_ops: List[dict] = []
+    packed_b: Dict[object, int] = {}
 
     def gemm_tables(c_idx, a: Node, b: Node):
         sa, sb, sc = _strides(g, a.idx), _strides(g, b.idx), _strides(g, c_idx)
@@ -291,6 +302,7 @@ def lower(g: CGraph, mode: str, dtype: str, nb: int = 1, emit_values: bool = Tru
             assert n.acc_into >= 0
             t = nodes[n.acc_into]
             body_ops.append(dict(kind="rgemm", g=(SP_GACC, base[t.id], -1), a=a_loc, d=d_loc,
+                                 rk=_pick_tile(g.size(k_idx), (4, 3, 2, 1)), rn=_pick_tile(g.size(c_idx), (4, 3, 2, 1)),
                                  nm=g.size(m_idx), nk=g.size(k_idx), nn=g.size(c_idx),
                                  am=_offsets(g, m_idx, sa), dm=_offsets(g, m_idx, sd),
                                  ak=_offsets(g, k_idx, sa), dn=_offsets(g, c_idx, sd),
@@ -302,9 +314,38 @@ def lower(g: CGraph, mode: str, dtype: str, nb: int = 1, emit_values: bool = Tru
                 a, b = (p, q) if g.size(p.idx) >= g.size(q.idx) else (q, p)
             else:
                 a, b = (p, q) if p.batched else (q, p)
-            a_loc, b_loc = operand_loc(a, True), operand_loc(b, True)
+            tb = gemm_tables(n.idx, a, b)
+            tn = _pick_tile(tb["nn"], (9, 8, 5, 4, 3, 2, 1))
+            a_loc = operand_loc(a, True)
+            extra = dict(tn=tn, ldb=0, packed=0)
+            if b.batched:
+                b_loc = operand_loc(b, True)
+            else:
+                # shared B: a PREP copy packed as [k][column group][TN padded to 16 bytes] so that the
+                # kernel fetches a thread's TN columns with aligned vector loads (broadcast)
+                vec = 4 if dtype == "f32" else 2
+                tnp = -(-tn // vec) * vec
+                ldb = (tb["nn"] // tn) * tnp
+                pkey = (b.id, tuple(tb["bk"]), tuple(tb["bn"]), tn)
+                if pkey not in packed_b:
+                    prog.const_elems = -(-prog.const_elems // 4) * 4
+                    pbase = prog.const_elems
+                    prog.const_elems += tb["nk"] * ldb
+                    sf = np.zeros(tb["nk"] * ldb, dtype=np.int64)
+                    cf = np.zeros(tb["nk"] * ldb, dtype=np.float64)
+                    for k in range(tb["nk"]):
+                        for c in range(tb["nn"]):
+                            at = k * ldb + (c // tn) * tnp + c % tn
+                            sf[at], cf[at] = tb["bk"][k] + tb["bn"][c], 1.0
+                    prep_ops.append(dict(kind="lin", acc=0, dst=(SP_CONST, pbase, -1), src=operand_loc(b, False),
+                                         count=tb["nk"] * ldb, sf=sf[:, None], cf=cf[:, None]))
+                    packed_b[pkey] = pbase
+                b_loc = (SP_CONST, packed_b[pkey], -1)
+                tb["bk"] = np.arange(tb["nk"], dtype=np.int64) * ldb
+                tb["bn"] = np.array([(c // tn) * tnp + c % tn for c in range(tb["nn"])], dtype=np.int64)
+                extra = dict(tn=tn, ldb=ldb, packed=1)
             dst, acc = dst_loc(n)
-            body_ops.append(dict(kind="gemm", acc=acc, c=dst, a=a_loc, b=b_loc, **gemm_tables(n.idx, a, b)))
+            body_ops.append(dict(kind="gemm", acc=acc, c=dst, a=a_loc, b=b_loc, **tb, **extra))
         else:
             a_loc, b_loc = operand_loc(p, False), operand_loc(q, False)
             dst, acc = dst_loc(n)
@@ -395,6 +436,7 @@ def lower(g: CGraph, mode: str, dtype: str, nb: int = 1, emit_values: bool = Tru
             w[8], w[9], w[10] = int(op["nm"]), int(op["nn"]), int(op["nk"])
             w[11], w[12], w[13] = tabs.ints(op["am"]), tabs.ints(op["cm"]), tabs.ints(op["ak"])
             w[14], w[15], w[16] = tabs.ints(op["bk"]), tabs.ints(op["bn"]), tabs.ints(op["cn"])
+            w[20], w[21], w[22] = int(op.get("tn", 0)), int(op.get("ldb", 0)), int(op.get("packed", 0))
         elif op["kind"] == "rgemm":
             w[0], w[1] = OP_RGEMM, 1
             w[2], w[3], _ = loc3(op["g"])
@@ -403,6 +445,7 @@ def lower(g: CGraph, mode: str, dtype: str, nb: int = 1, emit_values: bool = Tru
             w[8], w[9], w[10] = int(op["nm"]), int(op["nn"]), int(op["nk"])
             w[11], w[12], w[13] = tabs.ints(op["am"]), tabs.ints(op["dm"]), tabs.ints(op["ak"])
             w[14], w[15], w[16] = tabs.ints(op["dn"]), tabs.ints(op["gk"]), tabs.ints(op["gn"])
+            w[20], w[21] = int(op["rk"]), int(op["rn"])
         elif op["kind"] == "seed":
             w[0] = OP_SEED
             w[2] = int(op["cplx"])

@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <string>
@@ -33,8 +34,8 @@ namespace {
 constexpr int OP_WORDS = 24;
 constexpr int SP_CONST = 0, SP_FRAME = 1, SP_GIN = 2, SP_GOUT = 3, SP_GACC = 4;
 constexpr int OP_LIN = 1, OP_GEMM = 2, OP_RGEMM = 3, OP_SEED = 4;
-constexpr int THREADS = 256;
-constexpr int KTAB = 1024;  // staged (ak, bk) pairs per GEMM
+constexpr int THREADS = 256;           // PREP / FIN / reduce kernels
+constexpr int BODY_THREADS_MAX = 512;  // BODY kernel: 512 threads when one CTA owns the SM, else 256
 constexpr long long MAGIC = 0x544E5142323030LL;
 
 thread_local std::string g_error;
@@ -76,15 +77,63 @@ struct Prog {
 // ------------------------------------------------------------------------------------
 // BODY
 // ------------------------------------------------------------------------------------
+// All FRAME / CONST / GACC accesses of the hot loops go through 32-bit byte offsets that are
+// pre-scaled (element offset x S x sizeof(T)) when an op's tables are staged in shared memory,
+// so the inner loops are: one integer add + one ld.shared per A value, 16-byte broadcast loads
+// for the packed shared operand, FMAs -- and the epilogue is one add + one st.shared per output.
+constexpr int OTAB = 3072;  // ints of staged per-op tables
+
 template <typename T>
+__device__ __forceinline__ T lds(uint32_t a) {
+    T v;
+    if constexpr (sizeof(T) == 4)
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    else
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ void sts(uint32_t a, T v) {
+    if constexpr (sizeof(T) == 4)
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+    else
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+// 16-byte load into consecutive elements of o[]
+__device__ __forceinline__ void lds16(uint32_t a, float* o) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(a));
+}
+__device__ __forceinline__ void lds16(uint32_t a, double* o) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(a));
+}
+
+// FRAME accessor: shared memory (32-bit window address) or, for plans whose working set does
+// not fit, a per-CTA slab of global memory.
+template <typename T, bool SMEM>
+struct Frame;
+template <typename T>
+struct Frame<T, true> {
+    uint32_t base;
+    __device__ __forceinline__ T ld(uint32_t off) const { return lds<T>(base + off); }
+    __device__ __forceinline__ void st(uint32_t off, T v) const { sts<T>(base + off, v); }
+};
+template <typename T>
+struct Frame<T, false> {
+    char* base;
+    __device__ __forceinline__ T ld(uint32_t off) const { return *reinterpret_cast<const T*>(base + off); }
+    __device__ __forceinline__ void st(uint32_t off, T v) const { *reinterpret_cast<T*>(base + off) = v; }
+};
+
+template <typename T, bool SMEM>
 struct Tile {
-    T* cpool;        // CONST pool (shared memory copy)
-    T* gacc;         // per-CTA accumulators (shared memory)
-    T* frame;        // [frame_elems][S]
-    int2* ktab;      // staged per-k offsets of the current GEMM
+    Frame<T, SMEM> fr;
+    uint32_t cpool;   // shared-window byte address of the CONST pool
+    T* gacc;          // per-CTA accumulators (shared memory)
+    int* tab;         // staged tables of the current op (shared memory)
     int S, logS;
-    int nvalid;      // valid samples in this tile
-    long long s0;    // first global sample of the tile
+    uint32_t sbytes;  // S * sizeof(T): byte stride between consecutive elements of a buffer
+    int nvalid;       // valid samples in this tile
+    long long s0;     // first global sample of the tile
     int nb;
     T log_scale, inv_count;
 };
@@ -101,8 +150,9 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
-template <typename T>
-__device__ void body_lin(const Op& op, const Tile<T>& t, const Prog<T>& p, const RunArgs& args) {
+// dst[j] (=|+=) c0[j]*src[s0[j]] (+ c1[j]*src[s1[j]])
+template <typename T, bool SMEM>
+__device__ void body_lin(const Op& op, const Tile<T, SMEM>& t, const Prog<T>& p, const RunArgs& args) {
     const int acc = op.w[1], dsp = op.w[2], dbase = op.w[3], ssp = op.w[4], sbase = op.w[5];
     const int count = op.w[6], nt = op.w[7];
     const int* s0 = p.itab + op.w[9];
@@ -120,15 +170,14 @@ __device__ void body_lin(const Op& op, const Tile<T>& t, const Prog<T>& p, const
         const int s = i & (S - 1), j = i >> t.logS;
         const bool valid = s < t.nvalid;
         T v = T(0);
-#pragma unroll 2
         for (int term = 0; term < nt; ++term) {
             const int so = term == 0 ? __ldg(s0 + j) : __ldg(s1 + j);
             const T cf = term == 0 ? __ldg(c0 + j) : __ldg(c1 + j);
             T x;
             if (ssp == SP_FRAME) {
-                x = t.frame[(size_t)(sbase + so) * S + s];
+                x = t.fr.ld((uint32_t)((sbase + so) * S + s) * (uint32_t)sizeof(T));
             } else if (ssp == SP_CONST) {
-                x = t.cpool[sbase + so];
+                x = lds<T>(t.cpool + (uint32_t)(sbase + so) * (uint32_t)sizeof(T));
             } else if (src_batched_gin) {
                 x = valid ? __ldg(gsrc + sample_offset<T>(args, sslot, t.s0 + s, t.nb) + so) : T(0);
             } else {
@@ -137,8 +186,8 @@ __device__ void body_lin(const Op& op, const Tile<T>& t, const Prog<T>& p, const
             v += cf * x;
         }
         if (dsp == SP_FRAME) {
-            T* d = t.frame + (size_t)(dbase + j) * S + s;
-            *d = acc ? *d + v : v;
+            const uint32_t d = (uint32_t)((dbase + j) * S + s) * (uint32_t)sizeof(T);
+            t.fr.st(d, acc ? t.fr.ld(d) + v : v);
         } else if (valid) {  // batched GOUT, [nsamples][elems]
             T* d = gdst + (t.s0 + s) * (long long)delems + j;
             *d = acc ? *d + v : v;
@@ -146,10 +195,116 @@ __device__ void body_lin(const Op& op, const Tile<T>& t, const Prog<T>& p, const
     }
 }
 
+// ---- GEMM ---------------------------------------------------------------------------
 // C[cm[r]+cn[c]] (=|+=) sum_k A[am[r]+ak[k]] * B[bk[k]+bn[c]] for every sample of the tile.
-// Lanes run over samples, so A/C accesses are conflict free and a shared B is a broadcast.
-template <typename T, bool B_BATCHED>
-__device__ void body_gemm(const Op& op, const Tile<T>& t, const Prog<T>& p) {
+//
+// Thread mapping: one sample lane x RM rows x TN columns per thread (RM*TN accumulators in
+// registers).  Consecutive lanes are consecutive samples, so every A / C access of a warp is
+// 32 consecutive words (conflict free); the RM rows of a thread are strided by the number of
+// row groups so that, for tiles narrower than a warp, neighbouring lanes touch neighbouring
+// rows.  A shared B is read from its packed PREP copy with 16-byte vector loads that are a
+// broadcast for the warp; per k-step a thread issues RM + TN/4 shared loads for RM*TN FMAs.
+//
+// Staged tables (ints, byte offsets): [0,nm) am  [nm,2nm) cm  then bn[nn], cn[nn], ak[nk], bk[nk].
+template <typename T, bool SMEM, int RM, int TN, bool B_BATCHED>
+__device__ __forceinline__ void gemm_tile(const Op& op, const Tile<T, SMEM>& t) {
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int TNP = (TN + V - 1) / V * V;
+    const int acc = op.w[1];
+    const int nm = op.w[8], nn = op.w[9], nk = op.w[10];
+    const uint32_t ldb = (uint32_t)op.w[21] * (uint32_t)sizeof(T);
+    const int* am = t.tab;
+    const int* cm = am + nm;
+    const int* bn = cm + nm;
+    const int* cn = bn + nn;
+    const int* ak = cn + nn;
+    const int* bk = ak + nk;
+    const int nrg = (nm + RM - 1) / RM, ncg = nn / TN;
+    const int total = (nrg * ncg) << t.logS;
+    for (int it = threadIdx.x; it < total; it += blockDim.x) {
+        const uint32_t sb = (uint32_t)(it & (t.S - 1)) * (uint32_t)sizeof(T);
+        const int rc = it >> t.logS;
+        const int cg = rc / nrg, rg = rc - cg * nrg;
+        uint32_t aoff[RM];
+        int crow[RM];
+#pragma unroll
+        for (int j = 0; j < RM; ++j) {
+            const int r = rg + j * nrg;
+            const int rr = r < nm ? r : rg;
+            aoff[j] = (uint32_t)am[rr] + sb;
+            crow[j] = r < nm ? cm[rr] + (int)sb : -1;
+        }
+        T sum[RM][TN];
+#pragma unroll
+        for (int j = 0; j < RM; ++j)
+#pragma unroll
+            for (int i = 0; i < TN; ++i) sum[j][i] = T(0);
+        if (!B_BATCHED) {
+            uint32_t brow = t.cpool + (uint32_t)op.w[7] * (uint32_t)sizeof(T) + (uint32_t)(cg * TNP) * (uint32_t)sizeof(T);
+#pragma unroll 3
+            for (int k = 0; k < nk; ++k) {
+                const uint32_t ka = (uint32_t)ak[k];
+                T b[TNP];
+#pragma unroll
+                for (int i = 0; i < TNP; i += V) lds16(brow + (uint32_t)i * (uint32_t)sizeof(T), b + i);
+                brow += ldb;
+#pragma unroll
+                for (int j = 0; j < RM; ++j) {
+                    const T a = t.fr.ld(aoff[j] + ka);
+#pragma unroll
+                    for (int i = 0; i < TN; ++i) sum[j][i] = fma(a, b[i], sum[j][i]);
+                }
+            }
+        } else {
+            uint32_t boff[TN];
+#pragma unroll
+            for (int i = 0; i < TN; ++i) boff[i] = (uint32_t)bn[cg * TN + i] + sb;
+#pragma unroll 3
+            for (int k = 0; k < nk; ++k) {
+                const uint32_t ka = (uint32_t)ak[k], kb = (uint32_t)bk[k];
+                T b[TN];
+#pragma unroll
+                for (int i = 0; i < TN; ++i) b[i] = t.fr.ld(boff[i] + kb);
+#pragma unroll
+                for (int j = 0; j < RM; ++j) {
+                    const T a = t.fr.ld(aoff[j] + ka);
+#pragma unroll
+                    for (int i = 0; i < TN; ++i) sum[j][i] = fma(a, b[i], sum[j][i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TN; ++i) {
+            const int co = cn[cg * TN + i];
+#pragma unroll
+            for (int j = 0; j < RM; ++j) {
+                if (crow[j] >= 0) {
+                    const uint32_t d = (uint32_t)(crow[j] + co);
+                    t.fr.st(d, acc ? t.fr.ld(d) + sum[j][i] : sum[j][i]);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, bool SMEM, int TN, bool B_BATCHED>
+__device__ __forceinline__ void gemm_rows(const Op& op, const Tile<T, SMEM>& t) {
+    // rows per thread: as many as the register budget allows while every thread still has work
+    constexpr int RMAX = TN <= 4 ? 8 : 4;
+    const int nm = op.w[8], ncg = op.w[9] / TN;
+    int rm = RMAX;
+    while (rm > 2 && ((((nm + rm - 1) / rm) * ncg) << t.logS) < (int)blockDim.x) rm >>= 1;
+    if (RMAX == 8 && rm == 8)
+        gemm_tile<T, SMEM, (RMAX == 8 ? 8 : 4), TN, B_BATCHED>(op, t);
+    else if (rm >= 4)
+        gemm_tile<T, SMEM, 4, TN, B_BATCHED>(op, t);
+    else
+        gemm_tile<T, SMEM, 2, TN, B_BATCHED>(op, t);
+}
+
+// generic fallback (any shape, nothing staged)
+template <typename T, bool SMEM, bool B_BATCHED>
+__device__ void gemm_generic(const Op& op, const Tile<T, SMEM>& t, const Prog<T>& p) {
     const int acc = op.w[1], cbase = op.w[3], abase = op.w[5], bbase = op.w[7];
     const int nm = op.w[8], nn = op.w[9], nk = op.w[10];
     const int* am = p.itab + op.w[11];
@@ -159,109 +314,193 @@ __device__ void body_gemm(const Op& op, const Tile<T>& t, const Prog<T>& p) {
     const int* bn = p.itab + op.w[15];
     const int* cn = p.itab + op.w[16];
     const int S = t.S;
-    const bool staged = nk <= KTAB;
-    if (staged) {
-        for (int k = threadIdx.x; k < nk; k += blockDim.x)
-            t.ktab[k] = make_int2(__ldg(ak + k) * S, B_BATCHED ? __ldg(bk + k) * S : __ldg(bk + k));
-    }
-    __syncthreads();
-    const int nchunk = (nn + 3) >> 2;
-    const int total = (nchunk * nm) << t.logS;
+    const uint32_t es = (uint32_t)sizeof(T);
+    const int total = (nm * nn) << t.logS;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int s = i & (S - 1);
         const int rc = i >> t.logS;
-        const int r = rc % nm, c0 = (rc / nm) << 2;
-        const T* a_ptr = t.frame + (size_t)(abase + __ldg(am + r)) * S + s;
-        int bo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = min(c0 + j, nn - 1);
-            bo[j] = B_BATCHED ? (bbase + __ldg(bn + c)) * S + s : bbase + __ldg(bn + c);
+        const int r = rc % nm, c = rc / nm;
+        const int arow = abase + __ldg(am + r), bcol = bbase + __ldg(bn + c);
+        T sum = T(0);
+        for (int k = 0; k < nk; ++k) {
+            const T a = t.fr.ld((uint32_t)((arow + __ldg(ak + k)) * S + s) * es);
+            const T b = B_BATCHED ? t.fr.ld((uint32_t)((bcol + __ldg(bk + k)) * S + s) * es)
+                                  : lds<T>(t.cpool + (uint32_t)(bcol + __ldg(bk + k)) * es);
+            sum = fma(a, b, sum);
         }
-        const T* b_ptr = B_BATCHED ? t.frame : t.cpool;
-        T sum[4] = {T(0), T(0), T(0), T(0)};
-        if (staged) {
-#pragma unroll 3
-            for (int k = 0; k < nk; ++k) {
-                const int2 kb = t.ktab[k];
-                const T a = a_ptr[kb.x];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sum[j] = fma(a, b_ptr[bo[j] + kb.y], sum[j]);
-            }
-        } else {
-            for (int k = 0; k < nk; ++k) {
-                const int ka = __ldg(ak + k) * S, kbv = B_BATCHED ? __ldg(bk + k) * S : __ldg(bk + k);
-                const T a = a_ptr[ka];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sum[j] = fma(a, b_ptr[bo[j] + kbv], sum[j]);
-            }
+        const uint32_t d = (uint32_t)((cbase + __ldg(cm + r) + __ldg(cn + c)) * S + s) * es;
+        t.fr.st(d, acc ? t.fr.ld(d) + sum : sum);
+    }
+}
+
+template <typename T, bool SMEM, bool B_BATCHED>
+__device__ void body_gemm(const Op& op, const Tile<T, SMEM>& t, const Prog<T>& p) {
+    const int nm = op.w[8], nn = op.w[9], nk = op.w[10], tn = op.w[20];
+    if (2 * (nm + nn + nk) > OTAB || tn <= 0 || (!B_BATCHED && op.w[22] != 1)) {
+        gemm_generic<T, SMEM, B_BATCHED>(op, t, p);
+        return;
+    }
+    {   // stage this op's tables, pre-scaled to byte offsets
+        const int sb = (int)t.sbytes;
+        const int *am = p.itab + op.w[11], *cm = p.itab + op.w[12], *ak = p.itab + op.w[13];
+        const int *bk = p.itab + op.w[14], *bn = p.itab + op.w[15], *cn = p.itab + op.w[16];
+        const int cbase = op.w[3], abase = op.w[5], bbase = op.w[7];
+        int* tab = t.tab;
+        for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+            tab[i] = (abase + __ldg(am + i)) * sb;
+            tab[nm + i] = (cbase + __ldg(cm + i)) * sb;
         }
-        const int crow = cbase + __ldg(cm + r);
+        tab += 2 * nm;
+        for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+            tab[i] = B_BATCHED ? (bbase + __ldg(bn + i)) * sb : 0;
+            tab[nn + i] = __ldg(cn + i) * sb;
+        }
+        tab += 2 * nn;
+        for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+            tab[i] = __ldg(ak + i) * sb;
+            tab[nk + i] = B_BATCHED ? __ldg(bk + i) * sb : 0;
+        }
+    }
+    __syncthreads();
+    switch (tn) {
+        case 1: gemm_rows<T, SMEM, 1, B_BATCHED>(op, t); break;
+        case 2: gemm_rows<T, SMEM, 2, B_BATCHED>(op, t); break;
+        case 3: gemm_rows<T, SMEM, 3, B_BATCHED>(op, t); break;
+        case 4: gemm_rows<T, SMEM, 4, B_BATCHED>(op, t); break;
+        case 5: gemm_rows<T, SMEM, 5, B_BATCHED>(op, t); break;
+        case 8: gemm_rows<T, SMEM, 8, B_BATCHED>(op, t); break;
+        case 9: gemm_rows<T, SMEM, 9, B_BATCHED>(op, t); break;
+        default: gemm_generic<T, SMEM, B_BATCHED>(op, t, p); break;
+    }
+}
+
+// ---- RGEMM --------------------------------------------------------------------------
+// G[gk[i]+gn[c]] += sum over the tile's samples and rows r of A[am[r]+ak[i]] * D[dm[r]+dn[c]].
+// One warp owns an RK x RN output tile; its lanes split the (row, sample) pairs and combine
+// with a shuffle tree, so the accumulation order is fixed (deterministic).
+// Staged tables (byte offsets): am[nm], dm[nm].
+template <typename T, bool SMEM, int RK, int RN>
+__device__ __forceinline__ void rgemm_tile(const Op& op, const Tile<T, SMEM>& t, const Prog<T>& p) {
+    const int gbase = op.w[3], abase = op.w[5], dbase = op.w[7];
+    const int nm = op.w[8], nn = op.w[9], nk = op.w[10];
+    const int* ak = p.itab + op.w[13];
+    const int* dn = p.itab + op.w[14];
+    const int* gk = p.itab + op.w[15];
+    const int* gn = p.itab + op.w[16];
+    const int* am = t.tab;
+    const int* dm = am + nm;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int ntn = nn / RN, tiles = (nk / RK) * ntn;
+    const int rows = nm << t.logS;
+    const int sb = (int)t.sbytes;
+    for (int tile = warp; tile < tiles; tile += nwarp) {
+        const int i0 = (tile / ntn) * RK, c0 = (tile % ntn) * RN;
+        uint32_t aoff[RK], doff[RN];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (c0 + j < nn) {
-                T* d = t.frame + (size_t)(crow + __ldg(cn + c0 + j)) * S + s;
-                *d = acc ? *d + sum[j] : sum[j];
+        for (int i = 0; i < RK; ++i) aoff[i] = (uint32_t)((abase + __ldg(ak + i0 + i)) * sb);
+#pragma unroll
+        for (int j = 0; j < RN; ++j) doff[j] = (uint32_t)((dbase + __ldg(dn + c0 + j)) * sb);
+        T sum[RK][RN];
+#pragma unroll
+        for (int i = 0; i < RK; ++i)
+#pragma unroll
+            for (int j = 0; j < RN; ++j) sum[i][j] = T(0);
+#pragma unroll 2
+        for (int idx = lane; idx < rows; idx += 32) {
+            const uint32_t s4 = (uint32_t)(idx & (t.S - 1)) * (uint32_t)sizeof(T);
+            const int r = idx >> t.logS;
+            const uint32_t ra = (uint32_t)am[r] + s4, rd = (uint32_t)dm[r] + s4;
+            T a[RK], d[RN];
+#pragma unroll
+            for (int i = 0; i < RK; ++i) a[i] = t.fr.ld(aoff[i] + ra);
+#pragma unroll
+            for (int j = 0; j < RN; ++j) d[j] = t.fr.ld(doff[j] + rd);
+#pragma unroll
+            for (int i = 0; i < RK; ++i)
+#pragma unroll
+                for (int j = 0; j < RN; ++j) sum[i][j] = fma(a[i], d[j], sum[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < RK; ++i)
+#pragma unroll
+            for (int j = 0; j < RN; ++j) sum[i][j] = warp_sum(sum[i][j]);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < RK; ++i) {
+                const int grow = gbase + __ldg(gk + i0 + i);
+#pragma unroll
+                for (int j = 0; j < RN; ++j) t.gacc[grow + __ldg(gn + c0 + j)] += sum[i][j];
             }
         }
     }
 }
 
-// G[gk[i]+gn[c]] += sum over the tile's samples and rows r of A[am[r]+ak[i]] * D[dm[r]+dn[c]].
-// One warp owns an output strip; its lanes split (row, sample) pairs and combine
-// with a shuffle tree, so the accumulation order is fixed (deterministic).
-template <typename T>
-__device__ void body_rgemm(const Op& op, const Tile<T>& t, const Prog<T>& p) {
-    const int gbase = op.w[3], abase = op.w[5], dbase = op.w[7];
-    const int nm = op.w[8], nn = op.w[9], nk = op.w[10];
+template <typename T, bool SMEM, int RK>
+__device__ __forceinline__ void rgemm_cols(int rn, const Op& op, const Tile<T, SMEM>& t, const Prog<T>& p) {
+    switch (rn) {
+        case 4: rgemm_tile<T, SMEM, RK, 4>(op, t, p); break;
+        case 3: rgemm_tile<T, SMEM, RK, 3>(op, t, p); break;
+        case 2: rgemm_tile<T, SMEM, RK, 2>(op, t, p); break;
+        default: rgemm_tile<T, SMEM, RK, 1>(op, t, p); break;
+    }
+}
+
+template <typename T, bool SMEM>
+__device__ void body_rgemm(const Op& op, const Tile<T, SMEM>& t, const Prog<T>& p) {
+    const int nm = op.w[8];
+    int rk = op.w[20], rn = op.w[21];
+    if (rk < 1 || rk > 4 || op.w[10] % rk) rk = 1;
+    if (rn < 1 || rn > 4 || op.w[9] % rn) rn = 1;
     const int* am = p.itab + op.w[11];
     const int* dm = p.itab + op.w[12];
-    const int* ak = p.itab + op.w[13];
-    const int* dn = p.itab + op.w[14];
-    const int* gk = p.itab + op.w[15];
-    const int* gn = p.itab + op.w[16];
-    const int S = t.S;
+    const int sb = (int)t.sbytes;
+    if (2 * nm <= OTAB) {
+        for (int r = threadIdx.x; r < nm; r += blockDim.x) {
+            t.tab[r] = __ldg(am + r) * sb;
+            t.tab[nm + r] = __ldg(dm + r) * sb;
+        }
+        __syncthreads();
+        switch (rk) {
+            case 4: rgemm_cols<T, SMEM, 4>(rn, op, t, p); break;
+            case 3: rgemm_cols<T, SMEM, 3>(rn, op, t, p); break;
+            case 2: rgemm_cols<T, SMEM, 2>(rn, op, t, p); break;
+            default: rgemm_cols<T, SMEM, 1>(rn, op, t, p); break;
+        }
+        return;
+    }
+    // huge row counts: unstaged, one output per warp pass
+    const int gbase = op.w[3], abase = op.w[5], dbase = op.w[7], nn = op.w[9], nk = op.w[10];
+    const int *ak = p.itab + op.w[13], *dn = p.itab + op.w[14], *gk = p.itab + op.w[15], *gn = p.itab + op.w[16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int nchunk = (nn + 3) >> 2;
     const int rows = nm << t.logS;
-    for (int tile = warp; tile < nk * nchunk; tile += nwarp) {
-        const int i = tile / nchunk, c0 = (tile % nchunk) << 2;
-        const int aoff = abase + __ldg(ak + i);
-        int doff[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) doff[j] = dbase + __ldg(dn + min(c0 + j, nn - 1));
-        T sum[4] = {T(0), T(0), T(0), T(0)};
+    for (int o = warp; o < nk * nn; o += nwarp) {
+        const int i = o / nn, c = o % nn;
+        const int ao = abase + __ldg(ak + i), dof = dbase + __ldg(dn + c);
+        T sum = T(0);
         for (int idx = lane; idx < rows; idx += 32) {
-            const int s = idx & (S - 1), r = idx >> t.logS;
-            const T a = t.frame[(size_t)(aoff + __ldg(am + r)) * S + s];
-            const int dr = __ldg(dm + r);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sum[j] = fma(a, t.frame[(size_t)(doff[j] + dr) * S + s], sum[j]);
+            const int s = idx & (t.S - 1), r = idx >> t.logS;
+            sum = fma(t.fr.ld((uint32_t)((ao + __ldg(am + r)) * t.S + s) * (uint32_t)sizeof(T)),
+                      t.fr.ld((uint32_t)((dof + __ldg(dm + r)) * t.S + s) * (uint32_t)sizeof(T)), sum);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sum[j] = warp_sum(sum[j]);
-        if (lane == 0) {
-            const int grow = gbase + __ldg(gk + i);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (c0 + j < nn) t.gacc[grow + __ldg(gn + c0 + j)] += sum[j];
-        }
+        sum = warp_sum(sum);
+        if (lane == 0) t.gacc[gbase + __ldg(gk + i) + __ldg(gn + c)] += sum;
     }
 }
 
 // Fused loss (engine_siamese.py:490-530): value = v or |v|^2 ; loss += -(log(max(value,1e-10)) +
 // log_scale) / count ; d value = -1/(count*value) where value >= 1e-10 (torch.clamp passes the
 // gradient on the boundary), chained through |v|^2 for complex amplitudes.
-template <typename T>
-__device__ void body_seed(const Op& op, const Tile<T>& t) {
+template <typename T, bool SMEM>
+__device__ void body_seed(const Op& op, const Tile<T, SMEM>& t) {
     const int cplx = op.w[2], vb = op.w[3], dvb = op.w[4], lb = op.w[5];
     const int S = t.S;
+    const uint32_t es = (uint32_t)sizeof(T);
     if ((threadIdx.x >> 5) == 0) {
         T part = T(0);
         for (int s = threadIdx.x; s < S; s += 32) {
-            T vr = t.frame[(size_t)vb * S + s], vi = T(0), val;
+            T vr = t.fr.ld((uint32_t)(vb * S + s) * es), vi = T(0), val;
             if (cplx) {
-                vi = t.frame[(size_t)(vb + 1) * S + s];
+                vi = t.fr.ld((uint32_t)((vb + 1) * S + s) * es);
                 val = vr * vr + vi * vi;
             } else {
                 val = vr;
@@ -271,10 +510,10 @@ __device__ void body_seed(const Op& op, const Tile<T>& t) {
             if (valid) part -= (log(clamped) + t.log_scale) * t.inv_count;
             const T dval = (valid && val >= T(1e-10)) ? -t.inv_count / clamped : T(0);
             if (cplx) {
-                t.frame[(size_t)dvb * S + s] = dval * T(2) * vr;
-                t.frame[(size_t)(dvb + 1) * S + s] = dval * T(2) * vi;
+                t.fr.st((uint32_t)(dvb * S + s) * es, dval * T(2) * vr);
+                t.fr.st((uint32_t)((dvb + 1) * S + s) * es, dval * T(2) * vi);
             } else {
-                t.frame[(size_t)dvb * S + s] = dval;
+                t.fr.st((uint32_t)(dvb * S + s) * es, dval);
             }
         }
         part = warp_sum(part);
@@ -283,24 +522,28 @@ __device__ void body_seed(const Op& op, const Tile<T>& t) {
 }
 
 template <typename T, bool FRAME_SMEM>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(BODY_THREADS_MAX, 1)
 tnq_body_kernel(Prog<T> p, const __grid_constant__ RunArgs args, const T* __restrict__ constg,
                 T* __restrict__ partials, T* __restrict__ frame_g, long long nsamples, int S, int logS,
                 long long ntiles, T log_scale, T inv_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int2 ktab[KTAB];
+    __shared__ int otab[OTAB];
     T* cpool = reinterpret_cast<T*>(smem_raw);
     T* gacc = cpool + ((p.const_elems + 3) & ~3);
     T* frame_s = gacc + ((p.gacc_elems + 3) & ~3);
     for (int i = threadIdx.x; i < p.const_elems; i += blockDim.x) cpool[i] = constg[i];
     for (int i = threadIdx.x; i < p.gacc_elems; i += blockDim.x) gacc[i] = T(0);
-    Tile<T> t;
-    t.cpool = cpool;
+    Tile<T, FRAME_SMEM> t;
+    if constexpr (FRAME_SMEM)
+        t.fr.base = (uint32_t)__cvta_generic_to_shared(frame_s);
+    else
+        t.fr.base = reinterpret_cast<char*>(frame_g + (size_t)blockIdx.x * p.frame_elems * S);
+    t.cpool = (uint32_t)__cvta_generic_to_shared(cpool);
     t.gacc = gacc;
-    t.frame = FRAME_SMEM ? frame_s : frame_g + (size_t)blockIdx.x * p.frame_elems * S;
-    t.ktab = ktab;
+    t.tab = otab;
     t.S = S;
     t.logS = logS;
+    t.sbytes = (uint32_t)S * (uint32_t)sizeof(T);
     t.nb = p.nb;
     t.log_scale = log_scale;
     t.inv_count = inv_count;
@@ -313,19 +556,19 @@ tnq_body_kernel(Prog<T> p, const __grid_constant__ RunArgs args, const T* __rest
             const Op& op = p.ops[o];
             switch (op.w[0]) {
                 case OP_LIN:
-                    body_lin<T>(op, t, p, args);
+                    body_lin<T, FRAME_SMEM>(op, t, p, args);
                     break;
                 case OP_GEMM:
                     if (op.w[6] == SP_FRAME)
-                        body_gemm<T, true>(op, t, p);
+                        body_gemm<T, FRAME_SMEM, true>(op, t, p);
                     else
-                        body_gemm<T, false>(op, t, p);
+                        body_gemm<T, FRAME_SMEM, false>(op, t, p);
                     break;
                 case OP_RGEMM:
-                    body_rgemm<T>(op, t, p);
+                    body_rgemm<T, FRAME_SMEM>(op, t, p);
                     break;
                 case OP_SEED:
-                    body_seed<T>(op, t);
+                    body_seed<T, FRAME_SMEM>(op, t);
                     break;
                 default:
                     break;
@@ -444,7 +687,7 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Geometry {
-    int S = 0, logS = 0, grid = 0;
+    int S = 0, logS = 0, grid = 0, threads = 256;
     bool frame_smem = true;
     size_t smem = 0;
     long long ntiles = 0;
@@ -456,26 +699,36 @@ int plan_geometry(const tnq_plan* pl, long long nsamples, Geometry* g) {
     if (nsamples <= 0) return fail("nsamples must be positive");
     const size_t es = pl->elem_size();
     const size_t fixed = (align_up(pl->const_elems, 4) + align_up(pl->gacc_elems, 4)) * es;
-    const size_t budget = (size_t)pl->max_smem - KTAB * sizeof(int2) - 1024;
+    const size_t budget = (size_t)pl->max_smem - OTAB * sizeof(int) - 1024;
     if (fixed > budget)
         return fail("plan too large for the shared-memory contraction kernel: prepared cores + gradient "
                     "accumulators need " + std::to_string(fixed) + " bytes of shared memory");
-    // samples per tile: as many as fit, but keep at least one tile per SM
-    int want = 128;
-    while (want > 8 && nsamples / want < pl->sm_count) want >>= 1;
-    int S = want;
+    // Samples per tile.  Every op of the program costs two barriers and a table staging per
+    // tile, so tiles should be as large as possible while still giving every SM a tile; a large
+    // tile whose working set does not fit shared memory keeps its FRAME in a per-CTA global slab
+    // (L2 resident), which measured faster than small shared-memory tiles ("tiling").
+    int S = 256;
+    while (S > 8 && nsamples / S < pl->sm_count) S >>= 1;
     const size_t frame_per_sample = (size_t)(pl->frame_elems > 0 ? pl->frame_elems : 1) * es;
-    while (S >= 4 && fixed + frame_per_sample * S > budget) S >>= 1;
-    g->frame_smem = S >= 4;
-    if (!g->frame_smem) S = 32;
+    g->frame_smem = fixed + frame_per_sample * S <= budget;
+    if (!g->frame_smem && S > 64) S = 64;
+    // experiment knobs (not part of the API): TNQ_TILE=<pow2>, TNQ_FORCE_GLOBAL=1, TNQ_CTAS_PER_SM=<n>
+    if (const char* e = getenv("TNQ_FORCE_GLOBAL")) { if (atoi(e)) g->frame_smem = false; }
+    if (const char* e = getenv("TNQ_TILE")) {
+        int v = atoi(e);
+        if (v >= 4 && (v & (v - 1)) == 0 && (!g->frame_smem || fixed + frame_per_sample * v <= budget)) S = v;
+    }
     g->S = S;
     g->logS = 0;
     while ((1 << g->logS) < S) ++g->logS;
     g->ntiles = (nsamples + S - 1) / S;
     g->smem = fixed + (g->frame_smem ? frame_per_sample * S : 0);
-    int per_sm = (int)(budget / (g->smem + KTAB * sizeof(int2) + 1024));
+    int per_sm = (int)(budget / (g->smem + OTAB * sizeof(int) + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
+    g->threads = per_sm == 1 ? 512 : 256;   // registers allow 512 x 128 or 2 x 256 x 128 per SM
+    if (per_sm > 2) per_sm = 2;
+    if (const char* e = getenv("TNQ_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
     long long grid = (long long)pl->sm_count * per_sm;
     if (grid > g->ntiles) grid = g->ntiles;
     g->grid = (int)grid;
@@ -520,13 +773,13 @@ int run_typed(tnq_plan* pl, long long nsamples, const RunArgs& args, const doubl
         auto k = tnq_body_kernel<T, true>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-        k<<<g.grid, THREADS, g.smem, stream>>>(p, args, constg, pl->gacc_elems ? partials : nullptr, frame_g,
+        k<<<g.grid, g.threads, g.smem, stream>>>(p, args, constg, pl->gacc_elems ? partials : nullptr, frame_g,
                                                nsamples, g.S, g.logS, g.ntiles, ls, ic);
     } else {
         auto k = tnq_body_kernel<T, false>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-        k<<<g.grid, THREADS, g.smem, stream>>>(p, args, constg, pl->gacc_elems ? partials : nullptr, frame_g,
+        k<<<g.grid, g.threads, g.smem, stream>>>(p, args, constg, pl->gacc_elems ? partials : nullptr, frame_g,
                                                nsamples, g.S, g.logS, g.ntiles, ls, ic);
     }
     ++g_launches;
