@@ -81,6 +81,18 @@ int tnq_plan_run(tnq_plan_t* plan, int64_t nsamples, const void* const* in_ptrs,
                  const int64_t* in_stride_hi, const int64_t* in_stride_lo, void* const* out_ptrs,
                  const double* scalars, void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * Large-bond-dimension regime: one pairwise contraction of the sweep as a batched GEMM on the
+ * tcgen05 tensor cores with fp32-faithful 3xTF32 arithmetic (replaces the bmm that torch.einsum
+ * dispatches for greedy_strategy.py:940,959 when the bond dimension is 64-128):
+ *     C[b] (M x N, row major, ldc) (=|+=) A[b] (M x K, row major, lda) * B[b]^T,  B[b] is N x K (ldb)
+ * K, lda, ldb and the batch strides must be multiples of 4 floats; A and B 16-byte aligned.
+ * A batch stride of 0 shares that operand across the batch.
+ */
+int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                    int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
+                    int accumulate, void* stream);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t tnq_launch_count(void);
 

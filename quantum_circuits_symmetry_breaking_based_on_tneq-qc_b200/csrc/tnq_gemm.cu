@@ -1,0 +1,257 @@
+// tnq_gemm.cu -- batched fp32 GEMM on the 5th-generation tensor cores (tcgen05) with
+// fp32-faithful arithmetic: every operand is split on the fly into TF32 hi + lo parts and
+// each product is issued as three tcgen05.mma.kind::tf32 (hi*hi + hi*lo + lo*hi, "3xTF32"),
+// accumulated in fp32 in tensor memory (TMEM).
+//
+//     C[b] (M x N, row major, ldc)  (=|+=)  A[b] (M x K, row major, lda) * B[b]^T  (B[b] is N x K, ldb)
+//
+// Role in the contraction path: the large-bond-dimension regime (bond 64-128, complex64), where a
+// pairwise contraction of the greedy sweep (tneq_qc/contractor/greedy_strategy.py:940,959: one
+// torch.einsum per qubit group) is a real GEMM: rows = batch x kept indices, K = contracted
+// indices.  Complex contractions arrive here as real GEMMs of doubled K and N (2x2-real form).
+//
+// Kernel anatomy (one 128 x 128 output tile per CTA, 160 threads):
+//   warps 0-3  producers : 16-byte global loads of the fp32 A / B tiles, split into TF32 hi and
+//                          lo, stored to shared memory directly in the UMMA canonical K-major
+//                          layout (8-row x 16-byte core matrices, no swizzle), 3-stage ring,
+//                          fence.proxy.async + mbarrier arrive;
+//                          afterwards the epilogue: tcgen05.ld 32 lanes x 32 columns -> registers
+//                          -> 128-byte row segments in global memory;
+//   warp 4     MMA issuer: one elected lane waits on the stage's "full" mbarrier and issues
+//                          4 k-steps x 3 tcgen05.mma (M=128, N=128, K=8), then tcgen05.commit to
+//                          the stage's "empty" mbarrier; owns the TMEM allocation (128 columns).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "tneq_b200.h"
+
+extern int tnq_internal_fail(const std::string& msg);
+extern int tnq_internal_cuda_fail(cudaError_t e, const char* what);
+extern void tnq_internal_count_launch();
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;          // tile (BK floats = 128 bytes = 8 x 16-byte chunks)
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB, one of {A hi, A lo, B hi, B lo}
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // 64 KB
+constexpr int PRODUCERS = 128;
+constexpr int GEMM_THREADS = PRODUCERS + 32;
+constexpr uint32_t TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error traps (surfacing as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle: 8 rows x 16 bytes core matrices stored
+// contiguously (128 B); LBO = distance between the two 16-byte K chunks of one MMA (128 B here),
+// SBO = distance between 8-row groups (1024 B here).  (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(128 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;
+}
+
+// instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128 (InstrDescriptor bit layout)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_c),
+        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ float tf32_hi(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// one 8-row x 4-chunk unit of a tile: global (row, chunk) -> hi / lo tiles in canonical layout
+__device__ __forceinline__ void stage_unit(const float* __restrict__ src, long long ld, long long rows_left,
+                                           long long k_left, int unit, int lane, uint32_t hi_base, uint32_t lo_base) {
+    const int rg = unit >> 1, half = unit & 1;
+    const int r8 = lane & 7, c4 = lane >> 3;
+    const int row = rg * 8 + r8, chunk = half * 4 + c4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows_left && chunk * 4 < k_left) v = __ldg(reinterpret_cast<const float4*>(src + row * ld + chunk * 4));
+    float4 h, l;
+    h.x = tf32_hi(v.x), h.y = tf32_hi(v.y), h.z = tf32_hi(v.z), h.w = tf32_hi(v.w);
+    l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+    const uint32_t off = (uint32_t)(rg * 64 + chunk * 8 + r8) * 16u;
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_base + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_base + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, long long M,
+                       long long N, long long K, long long lda, long long ldb, long long ldc, long long strideA,
+                       long long strideB, long long strideC, int accumulate) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bars[2 * STAGES + 1];
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * BN;
+    A += (long long)blockIdx.z * strideA + m0 * lda;
+    B += (long long)blockIdx.z * strideB + n0 * ldb;
+    C += (long long)blockIdx.z * strideC;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, PRODUCERS);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+    const int nkb = (int)((K + BK - 1) / BK);
+
+    if (warp < 4) {
+        // ---------------- producers ----------------
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+            mbar_wait(empty0 + 8 * s, phase ^ 1u);
+            const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
+            const long long k0 = (long long)kb * BK;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int unit = warp * 8 + i;
+                stage_unit(A + k0, lda, M - m0, K - k0, unit, lane, st, st + TILE_BYTES);
+                stage_unit(B + k0, ldb, N - n0, K - k0, unit, lane, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
+            mbar_arrive(full0 + 8 * s);
+        }
+        // ---------------- epilogue ----------------
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long row = m0 + warp * 32 + lane;
+        float* crow = C + row * ldc + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const long long col = n0 + c0 + j;
+                    if (col < N) {
+                        const float v = __uint_as_float(r[j]);
+                        crow[c0 + j] = accumulate ? crow[c0 + j] + v : v;
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ---------------- MMA issuer ----------------
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+            mbar_wait(full0 + 8 * s, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < BK / 8; ++j) {
+                    const uint32_t ko = (uint32_t)j * 2u * 128u;     // two 16-byte chunks per K=8 step
+                    const uint64_t a_hi = umma_desc(st + ko), a_lo = umma_desc(st + TILE_BYTES + ko);
+                    const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES + ko), b_lo = umma_desc(st + 3 * TILE_BYTES + ko);
+                    umma_tf32(tmem_base, a_lo, b_hi, (kb | j) != 0);
+                    umma_tf32(tmem_base, a_hi, b_lo, 1u);
+                    umma_tf32(tmem_base, a_hi, b_hi, 1u);
+                }
+                umma_commit(empty0 + 8 * s);                          // frees the stage when the MMAs retire
+                if (kb == nkb - 1) umma_commit(accum_bar);            // accumulator complete
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace
+
+extern "C" int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                               int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB,
+                               int64_t strideC, int accumulate, void* stream) {
+    if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || batch <= 0) return tnq_internal_fail("tnq_gemm_tf32x3: bad arguments");
+    if ((K & 3) || (lda & 3) || (ldb & 3) || (strideA & 3) || (strideB & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15))
+        return tnq_internal_fail("tnq_gemm_tf32x3: K, lda, ldb, batch strides must be multiples of 4 floats and A, B "
+                                 "16-byte aligned");
+    if (batch > 65535) return tnq_internal_fail("tnq_gemm_tf32x3: batch too large for one launch (max 65535)");
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+    cudaError_t e = cudaFuncSetAttribute(tnq_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(gemm)");
+    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
+    tnq_gemm_tf32x3_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(A, B, C, M, N, K, lda, ldb, ldc, strideA,
+                                                                                 strideB, strideC, accumulate);
+    tnq_internal_count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_gemm_tf32x3 launch");
+    return 0;
+}

@@ -662,6 +662,11 @@ tnq_fin_kernel(Prog<T> p, const __grid_constant__ RunArgs args, T* constg, T* ga
 
 }  // namespace
 
+// shared with the other translation units of the library (tnq_gemm.cu, tnq_permute.cu)
+int tnq_internal_fail(const std::string& msg) { return fail(msg); }
+int tnq_internal_cuda_fail(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+void tnq_internal_count_launch() { ++g_launches; }
+
 // ------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------

@@ -1,0 +1,67 @@
+"""tcgen05 3xTF32 GEMM (tnq_gemm_tf32x3) against a float64 torch reference.
+
+Tolerance: 3xTF32 keeps ~21 mantissa bits per product; with fp32 accumulation the result must
+be within 1e-5 of the float64 product relative to the largest entry (north_star's bound), and in
+practice lands near plain fp32 (few 1e-7)."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(A, B, C=None, accumulate=False):
+    """A: [b, M, K] (or [M, K]) row-major, B: [b, N, K]; returns C [b, M, N] = A @ B^T."""
+    from tneq_b200 import _lib
+    lib = _lib.load()
+    A3 = A if A.dim() == 3 else A[None]
+    B3 = B if B.dim() == 3 else B[None]
+    nb = max(A3.shape[0], B3.shape[0])
+    M, K = A3.shape[-2:]
+    N = B3.shape[-2]
+    if C is None:
+        C = torch.empty(nb, M, N, device=A.device, dtype=torch.float32)
+    sA = A3.stride(0) if A3.shape[0] > 1 else 0
+    sB = B3.stride(0) if B3.shape[0] > 1 else 0
+    rc = lib.tnq_gemm_tf32x3(ctypes.c_void_p(A3.data_ptr()), ctypes.c_void_p(B3.data_ptr()), ctypes.c_void_p(C.data_ptr()),
+                             M, N, K, A3.stride(-2), B3.stride(-2), C.stride(-2), nb, sA, sB, C.stride(0),
+                             1 if accumulate else 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc)
+    return C
+
+
+@pytest.mark.parametrize("M,N,K,nb", [(128, 128, 32, 1), (128, 128, 128, 1), (256, 384, 96, 1), (100, 72, 36, 1),
+                                      (1, 8, 4, 1), (300, 130, 260, 3), (4096, 128, 128, 2), (64, 8192, 128, 1)])
+def test_gemm_matches_float64(M, N, K, nb, built_lib):
+    torch.manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(nb, M, K, device="cuda")
+    B = torch.randn(nb, N, K, device="cuda")
+    C = _gemm(A, B)
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().transpose(-1, -2)
+    err = ((C.double() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1e-5, err
+    torch.backends.cuda.matmul.allow_tf32 = False
+    fp32 = ((A @ B.transpose(-1, -2)).double() - ref).abs().max() / ref.abs().max()
+    assert err < 20 * fp32.item() + 1e-7        # fp32-faithful, not TF32-grade (1e-3)
+
+
+def test_gemm_shared_operand_strides_and_accumulate(built_lib):
+    torch.manual_seed(5)
+    nb, M, N, K = 5, 96, 40, 64
+    Abig = torch.randn(nb, M, K + 12, device="cuda")
+    A = Abig[:, :, :K]                                   # lda > K
+    B = torch.randn(N, K, device="cuda")                 # shared across the batch (stride 0)
+    C0 = torch.randn(nb, M, N, device="cuda")
+    C = _gemm(A, B, C0.clone(), accumulate=True)
+    torch.cuda.synchronize()
+    ref = C0.double() + A.double() @ B.double().T
+    assert ((C.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+def test_gemm_rejects_unaligned(built_lib):
+    A = torch.randn(8, 6, device="cuda")
+    B = torch.randn(8, 6, device="cuda")
+    with pytest.raises(RuntimeError, match="multiples of 4"):
+        _gemm(A, B)

@@ -129,7 +129,7 @@ def test_compute_function_refuses_cpu_tensors():
 
 def test_c_abi_library_exports_every_declared_symbol(built_lib):
     header = open(os.path.join(ROOT, "include", "tneq_b200.h")).read()
-    declared = sorted(set(re.findall(r"\b(tnq_[a-z_]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"\b(tnq_[a-z0-9_]+)\s*\(", header)))
     assert "tnq_plan_run" in declared and "tnq_plan_create" in declared
     lib = ctypes.CDLL(built_lib)
     for name in declared:
