@@ -86,12 +86,35 @@ int tnq_plan_run(tnq_plan_t* plan, int64_t nsamples, const void* const* in_ptrs,
  * tcgen05 tensor cores with fp32-faithful 3xTF32 arithmetic (replaces the bmm that torch.einsum
  * dispatches for greedy_strategy.py:940,959 when the bond dimension is 64-128):
  *     C[b] (M x N, row major, ldc) (=|+=) A[b] (M x K, row major, lda) * B[b]^T,  B[b] is N x K (ldb)
- * K, lda, ldb and the batch strides must be multiples of 4 floats; A and B 16-byte aligned.
+ * Operands whose K, leading dimensions, batch strides (multiples of 4 floats) and base addresses
+ * (16 bytes) are aligned take 16-byte loads; anything else works through guarded scalar loads.
  * A batch stride of 0 shares that operand across the batch.
  */
 int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                     int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
                     int accumulate, void* stream);
+
+/*
+ * Index permutation / merge / split of a dense fp32 tensor (what torch.einsum does around every
+ * bmm, greedy_strategy.py:940,959; cf. tools/stage3_memory_permute/test_transpose_cost.py).
+ * `out` is compact row-major over out_dims[ndim]; in_strides[d] is the stride, in floats, of
+ * output dimension d in `in`.  The innermost `vec` floats (1, 2 = one complex number, or 4)
+ * move together and must be contiguous on both sides.  conj != 0 negates the imaginary parts.
+ */
+int tnq_permute_f32(const float* in, float* out, int ndim, const int64_t* out_dims, const int64_t* in_strides,
+                    int vec, int conj, void* stream);
+
+/*
+ * Complex -> 2x2-real expansion fused with a permutation:
+ *   out[..., ri, ..., ro] = E[ri][ro][c] * in[..., c],  E = [[re, im], [-im, re]]
+ * ri_dim / ro_dim are the positions of the two extra (extent-2) output dimensions; their
+ * in_strides entries are ignored; `in`'s (re, im) pair is contiguous.  conj conjugates `in`.
+ * tnq_cplx_fold_f32 is its adjoint (gradient path): out[..., c] (=|+=) sum over ri ^ ro == c.
+ */
+int tnq_cplx_expand_f32(const float* in, float* out, int ndim, const int64_t* out_dims, const int64_t* in_strides,
+                        int ri_dim, int ro_dim, int conj, void* stream);
+int tnq_cplx_fold_f32(const float* in, float* out, int ndim, const int64_t* out_dims, const int64_t* in_strides,
+                      int64_t ri_stride, int64_t ro_stride, int conj, int accumulate, void* stream);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t tnq_launch_count(void);

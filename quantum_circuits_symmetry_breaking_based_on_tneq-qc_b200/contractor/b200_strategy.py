@@ -56,12 +56,30 @@ def _real_view(t: torch.Tensor) -> torch.Tensor:
     return torch.view_as_real(t) if t.is_complex() else t
 
 
+# Cores bigger than this (real elements) do not fit the shared-memory VM: the sweep is then
+# executed contraction by contraction on the tcgen05 GEMM path (gemm_path.py).
+VM_MAX_CORE_ELEMS = 4096
+
+
 class _Bound:
     """One plan bound to one device: lowered programs are created lazily."""
 
     def __init__(self, plan: ContractionPlan, device: torch.device):
+        import os
         self.plan, self.device = plan, device
         self._dev: Dict[str, DeviceProgram] = {}
+        self._gemm: Dict[str, object] = {}
+        biggest = max(int(torch.tensor(s).prod()) for s in plan.core_shapes.values()) * (2 if plan.complex_mode else 1)
+        self.use_gemm_path = biggest > VM_MAX_CORE_ELEMS or os.environ.get("TNQ_FORCE_GEMM_PATH") == "1"
+        if self.use_gemm_path and plan.real_dtype != "f32":
+            raise NotImplementedError("large-bond contraction runs on the tensor cores in float32 / complex64 only; "
+                                      f"got {plan.dtype} with a core of {biggest} elements")
+
+    def gemm_runner(self, mode: str):
+        from .gemm_path import GemmPathRunner
+        if mode not in self._gemm:
+            self._gemm[mode] = GemmPathRunner(self.plan.graph(mode), self.device)
+        return self._gemm[mode]
 
     def program(self, mode: str) -> DeviceProgram:
         if mode not in self._dev:
@@ -132,12 +150,48 @@ class _Call:
             return torch.view_as_complex(flat.reshape(lead + body + [2]))
         return flat.reshape(lead + body)
 
+    # ---- large-bond route: node-by-node on the tcgen05 GEMM path ------------------------------
+    def _gemm_inputs(self, cores):
+        out = {}
+        for key, c in zip(self.core_keys, cores):
+            out[key] = _real_view(c.detach().contiguous())
+        for q, s_ in self.states.items():
+            out[("state", q)] = _real_view(s_.detach().contiguous())
+        for q, m in self.mxs.items():
+            m = m.detach()
+            if m.shape[0] == 1 and self.B != 1:
+                m = m.expand(self.B, *m.shape[1:])
+            if self.nb == 2 and m.dim() == 3:
+                m = m.unsqueeze(1).expand(-1, 2, -1, -1)
+            out[("mx", q)] = _real_view(m.contiguous()).reshape(self.nsamples, -1)
+        return out
+
+    def _gemm_forward(self, cores):
+        r = self.bound.gemm_runner("fwd")
+        val, lay = r.run(self._gemm_inputs(cores), self.B, self.nb, with_adjoint=False)
+        return self._shape_result(val[r.g.result].reshape(self.nsamples, -1))
+
+    def _gemm_backward(self, cores, seed):
+        r = self.bound.gemm_runner("bwd")
+        val, lay = r.run(self._gemm_inputs(cores), self.B, self.nb, with_adjoint=True, seed=seed)
+        grads = []
+        for key, c in zip(self.core_keys, cores):
+            gflat = val[r.g.grads[key]]
+            grads.append(torch.view_as_complex(gflat.reshape(tuple(c.shape) + (2,))) if c.is_complex()
+                         else gflat.reshape(c.shape))
+        return grads, val[r.g.result]
+
     def forward(self, cores):
+        if self.bound.use_gemm_path:
+            return self._gemm_forward(cores)
         prog = self.bound.program("fwd")
         (flat,) = prog.run(self.nsamples, self._inputs(prog, cores))
         return self._shape_result(flat)
 
     def backward(self, cores, grad_out):
+        if self.bound.use_gemm_path:
+            seed = _real_view(grad_out.contiguous()).reshape(self.nsamples, -1).to(torch.float32).contiguous()
+            return self._gemm_backward(cores, seed)[0]
         prog = self.bound.program("bwd")
         seed = _real_view(grad_out.contiguous()).reshape(self.nsamples, -1).to(prog.real_dtype).contiguous()
         outs = prog.run(self.nsamples, self._inputs(prog, cores, seed=seed))
@@ -155,6 +209,27 @@ class _Call:
 
     def train(self, cores, log_scale: float):
         """Fused forward + loss + reverse sweep.  Returns (loss, grads, values)."""
+        if self.bound.use_gemm_path:
+            # forward nodes, then the loss seed from the forward result (element-wise, torch), then the
+            # adjoint nodes -- one walk over the graph
+            box = {}
+            inv = 1.0 / self.nsamples
+
+            def seed_fn(res, layout):
+                flat = res.reshape(self.nsamples, -1)
+                if flat.shape[1] == 2 and self.bound.plan.complex_mode:
+                    val = flat[:, 0] * flat[:, 0] + flat[:, 1] * flat[:, 1]
+                else:
+                    val = flat[:, 0]
+                clamped = torch.clamp(val, min=1e-10)
+                box["loss"] = -(torch.log(clamped) + log_scale).sum() * inv
+                dval = torch.where(val >= 1e-10, -inv / clamped, torch.zeros_like(val))
+                if flat.shape[1] == 2 and self.bound.plan.complex_mode:
+                    return (flat * (2.0 * dval)[:, None]).contiguous()
+                return dval[:, None].contiguous()
+
+            grads, res = self._gemm_backward(cores, seed_fn)
+            return box["loss"], grads, self._shape_result(res.reshape(self.nsamples, -1))
         prog = self.bound.program("train")
         outs = prog.run(self.nsamples, self._inputs(prog, cores), scalars=(log_scale, 1.0 / self.nsamples))
         loss = outs[prog.prog.output_index(("loss", 0))][0]

@@ -48,8 +48,10 @@ class Node:
     p: int = -1                     # contract / lin source
     q: int = -1
     reduce_batch: bool = False      # contract of two batched tensors summed over samples
-    src_flat: Optional[np.ndarray] = None   # lin: [ndst, T] flat source positions
-    coef: Optional[np.ndarray] = None       # lin: [ndst, T]
+    lin_kind: str = ""              # lin: permute | conj | expand | fold | table  (tables are built lazily:
+    lin_args: tuple = ()            #      large-bond tensors never materialise them, see CGraph.lin_tables)
+    src_flat: Optional[np.ndarray] = None   # lin 'table': [ndst, T] flat source positions
+    coef: Optional[np.ndarray] = None       # lin 'table': [ndst, T]
     acc_into: int = -1              # adjoint contribution accumulated into that node's buffer
     is_accum: bool = False          # zero-initialised accumulation buffer (shared adjoints)
     role: str = "fwd"               # fwd | adj
@@ -109,53 +111,72 @@ class CGraph:
             self.flops_shared += 2.0 * work
         return n
 
-    def add_lin(self, src: Node, dst_idx, src_flat, coef, role="fwd", cplx=False, batched=None) -> Node:
-        src_flat = np.asarray(src_flat, dtype=np.int64)
-        coef = np.asarray(coef, dtype=np.float64)
-        if src_flat.ndim == 1:
-            src_flat, coef = src_flat[:, None], coef[:, None]
-        assert src_flat.shape == coef.shape and src_flat.shape[0] == self.size(dst_idx)
+    def add_lin(self, src: Node, dst_idx, kind: str, args=(), role="fwd", cplx=False, batched=None,
+                src_flat=None, coef=None) -> Node:
         return self._add(kind="lin", idx=tuple(dst_idx), batched=src.batched if batched is None else batched,
-                         cplx=cplx, needs_grad=src.needs_grad, p=src.id, src_flat=src_flat, coef=coef, role=role)
+                         cplx=cplx, needs_grad=src.needs_grad, p=src.id, lin_kind=kind, lin_args=tuple(args),
+                         src_flat=src_flat, coef=coef, role=role)
 
     # ---- elementary linear maps ---------------------------------------------
-    def _flat_of(self, idx_from, idx_to, fixed=None):
-        """For every element of a tensor laid out with index order `idx_to`, the
-        flat position of the same element in layout `idx_from`; indices of
-        idx_from missing from idx_to take their value from `fixed`."""
+    def _flat_of(self, idx_from, idx_to):
+        """For every element of a tensor laid out with index order `idx_to`, the flat
+        position of the same element in layout `idx_from` (same index set)."""
         shp = self.shape(idx_to)
         grids = np.indices(shp).reshape(len(shp), -1) if shp else np.zeros((0, 1), dtype=np.int64)
         pos = {i: k for k, i in enumerate(idx_to)}
         flat = np.zeros(grids.shape[1] if shp else 1, dtype=np.int64)
         stride = 1
         for i in reversed(idx_from):
-            v = grids[pos[i]] if i in pos else fixed[i]
-            flat = flat + v * stride
+            flat = flat + grids[pos[i]] * stride
             stride *= self.dims[i]
         return flat
 
     def lin_permute(self, src: Node, dst_idx, role="fwd") -> Node:
-        flat = self._flat_of(src.idx, dst_idx)
-        return self.add_lin(src, dst_idx, flat, np.ones_like(flat, dtype=np.float64), role=role, cplx=src.cplx)
+        return self.add_lin(src, dst_idx, "permute", role=role, cplx=src.cplx)
 
-    def lin_conj(self, src: Node) -> Node:
+    def lin_conj(self, src: Node, role="fwd") -> Node:
         assert src.cplx
-        flat = np.arange(self.size(src.idx), dtype=np.int64)
-        coef = np.where(flat % 2 == 0, 1.0, -1.0)
-        return self.add_lin(src, src.idx, flat, coef, cplx=True)
+        return self.add_lin(src, src.idx, "conj", role=role, cplx=True)
 
     def lin_expand(self, src: Node, ri_in: int, ro: int) -> Node:
         """Qx[x..., ri, ro] = E[ri, ro, c] Q[x..., c] with E the 2x2 real form of a
         complex scalar: [[re, im], [-im, re]] (rows ri, columns ro)."""
         assert src.cplx
-        body = src.idx[:-1]
-        n = self.size(body)
-        base = np.arange(n, dtype=np.int64)[:, None] * 2                  # position of (x, c=0)
-        c_of = np.array([0, 1, 1, 0], dtype=np.int64)[None, :]           # (ri,ro) -> c
-        sg = np.array([1.0, 1.0, -1.0, 1.0])[None, :]
-        flat = (base + c_of).reshape(-1)
-        coef = np.broadcast_to(sg, (n, 4)).reshape(-1)
-        return self.add_lin(src, tuple(body) + (ri_in, ro), flat, coef, cplx=False)
+        return self.add_lin(src, tuple(src.idx[:-1]) + (ri_in, ro), "expand", cplx=False)
+
+    def lin_fold(self, g_expanded: Node, like: Node, role="adj") -> Node:
+        """Adjoint of lin_expand: dQ[x..., c] from dQx[x..., ri, ro]."""
+        return self.add_lin(g_expanded, like.idx, "fold", role=role, cplx=True)
+
+    def lin_tables(self, n: Node):
+        """(src_flat [ndst, T], coef [ndst, T]) of a lin node -- only the shared-memory VM path
+        asks for them; tensors are small there."""
+        src = self.nodes[n.p]
+        nd = self.size(n.idx)
+        if n.lin_kind == "table":
+            return n.src_flat, n.coef
+        if n.lin_kind == "permute":
+            flat = self._flat_of(src.idx, n.idx)
+            return flat[:, None], np.ones((nd, 1))
+        if n.lin_kind == "conj":
+            flat = np.arange(nd, dtype=np.int64)
+            return flat[:, None], np.where(flat % 2 == 0, 1.0, -1.0)[:, None]
+        if n.lin_kind == "expand":
+            nb = self.size(src.idx[:-1])
+            base = np.arange(nb, dtype=np.int64)[:, None] * 2
+            c_of = np.array([0, 1, 1, 0], dtype=np.int64)[None, :]          # (ri, ro) -> c
+            sg = np.array([1.0, 1.0, -1.0, 1.0])[None, :]
+            return (base + c_of).reshape(-1)[:, None], np.broadcast_to(sg, (nb, 4)).reshape(-1)[:, None]
+        if n.lin_kind == "fold":
+            nb = nd // 2
+            base = np.arange(nb, dtype=np.int64)[:, None] * 4                 # position of (x, ri=0, ro=0)
+            # c = 0: (0,0) + (1,1) ; c = 1: (0,1) - (1,0)
+            s0 = (base + np.array([0, 1])[None, :]).reshape(-1)
+            s1 = (base + np.array([3, 2])[None, :]).reshape(-1)
+            c0 = np.ones(nd)
+            c1 = np.tile(np.array([1.0, -1.0]), nb)
+            return np.stack([s0, s1], axis=1), np.stack([c0, c1], axis=1)
+        raise ValueError(n.lin_kind)
 
     # ---- complex-aware contraction -------------------------------------------
     def contract(self, p: Node, q: Node) -> Node:
@@ -421,20 +442,14 @@ def add_backward(g: CGraph, seed_from: str):
             src = g.nodes[node.p]
 
             def make(acc, src=src, node=node):
-                nsrc = g.size(src.idx)
-                rows = [[] for _ in range(nsrc)]
-                for d in range(node.src_flat.shape[0]):
-                    for t in range(node.src_flat.shape[1]):
-                        if node.coef[d, t] != 0.0:
-                            rows[int(node.src_flat[d, t])].append((d, float(node.coef[d, t])))
-                width = max(1, max(len(r) for r in rows))
-                assert width <= 2, "adjoint of a linear map with more than two terms"
-                sf = np.zeros((nsrc, width), dtype=np.int64)
-                cf = np.zeros((nsrc, width), dtype=np.float64)
-                for j, r in enumerate(rows):
-                    for t, (d, c) in enumerate(r):
-                        sf[j, t], cf[j, t] = d, c
-                c = g.add_lin(gnode, src.idx, sf, cf, role="adj", cplx=src.cplx, batched=gnode.batched)
+                if node.lin_kind == "permute":
+                    c = g.lin_permute(gnode, src.idx, role="adj")
+                elif node.lin_kind == "conj":
+                    c = g.lin_conj(gnode, role="adj")
+                elif node.lin_kind == "expand":
+                    c = g.lin_fold(gnode, src)
+                else:
+                    raise NotImplementedError(f"adjoint of lin '{node.lin_kind}'")
                 c.acc_into, c.needs_grad = acc, False
                 return c
 

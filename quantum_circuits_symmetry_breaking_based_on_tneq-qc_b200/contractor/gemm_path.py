@@ -1,0 +1,235 @@
+"""Large-bond-dimension execution of a contraction graph: permute -> tcgen05 GEMM.
+
+The shared-memory VM (vm_program.py / csrc/tnq_vm.cu) keeps every prepared core in shared
+memory, which stops working once cores have 64^4 elements.  In that regime every pairwise
+contraction of the sweep is a real GEMM, so the same contraction graph (cgraph.py) is executed
+node by node on global-memory tensors:
+
+    contract   ->  [tnq_permute_f32 to put the contracted indices innermost, only if needed]
+                   tnq_gemm_tf32x3   (tcgen05, fp32-faithful 3xTF32, TMEM accumulators)
+    lin        ->  tnq_permute_f32 (permute / conj), tnq_cplx_expand_f32, tnq_cplx_fold_f32
+    reduce over the batch (core gradients) -> the batch is folded into the GEMM's K dimension
+
+float32 / complex64 only (tensor cores); complex contractions are real GEMMs of the operand
+against the 2x2-real expansion of the other (see cgraph.py).  PyTorch provides the buffers
+and the stream; all arithmetic on tensors is done by the kernels named above.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int64, c_void_p
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import _lib
+from .cgraph import CGraph, Node
+
+BATCH = -1   # pseudo index id of the sample dimension in layouts
+
+
+class GemmPathRunner:
+    def __init__(self, graph: CGraph, device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("the GEMM path runs on CUDA devices only (no CPU fallback)")
+        self.g, self.device = graph, device
+        self.lib = _lib.load()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.tnq_device_check())
+        self.flops = 0.0
+
+    # ---- raw kernel calls ------------------------------------------------------------
+    def _stream(self):
+        return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _permute(self, src: torch.Tensor, src_strides: Sequence[int], out_dims: Sequence[int], vec: int, conj: bool):
+        out = torch.empty(tuple(out_dims), dtype=torch.float32, device=self.device)
+        n = len(out_dims)
+        _lib.check(self.lib.tnq_permute_f32(c_void_p(src.data_ptr()), c_void_p(out.data_ptr()), n,
+                                            (c_int64 * n)(*out_dims), (c_int64 * n)(*src_strides), vec, int(conj),
+                                            self._stream()))
+        return out
+
+    def _gemm(self, A, B, C, M, N, K, lda, ldb, ldc, batch=1, sA=0, sB=0, sC=0, accumulate=False):
+        _lib.check(self.lib.tnq_gemm_tf32x3(c_void_p(A.data_ptr()), c_void_p(B.data_ptr()), c_void_p(C.data_ptr()),
+                                            M, N, K, lda, ldb, ldc, batch, sA, sB, sC, int(accumulate), self._stream()))
+        self.flops += 2.0 * M * N * K * batch
+
+    # ---- layouts --------------------------------------------------------------------------
+    def _extent(self, i, B):
+        return B if i == BATCH else self.g.dims[i]
+
+    def _size(self, idx, B):
+        n = 1
+        for i in idx:
+            n *= self._extent(i, B)
+        return n
+
+    def _arrange(self, t: torch.Tensor, layout: List[int], rows: List[int], cols: List[int], B: int,
+                 exact: bool = False):
+        """Bring `t` (index order `layout`) into the form [rows..., cols...]: `cols` in exactly the
+        given order, `rows` in any order (their current order is kept when no copy is needed)
+        unless exact.  Returns (tensor, order of the row indices).  At most one permute kernel."""
+        k = len(cols)
+        head, tail = layout[: len(layout) - k], layout[len(layout) - k:]
+        if tail == list(cols) and (head == list(rows) if exact else sorted(head) == sorted(rows)):
+            return t, head
+        new_layout = list(rows) + list(cols)
+        strides, s = {}, 1
+        for i in reversed(layout):
+            strides[i] = s
+            s *= self._extent(i, B)
+        dims = [self._extent(i, B) for i in new_layout]
+        st = [strides[i] for i in new_layout]
+        if not dims:
+            return t, []
+        # complex pairs travel together when (re, im) is innermost on both sides
+        vec = 2 if (dims[-1] == 2 and st[-1] == 1 and len(dims) > 1 and all(x % 2 == 0 for x in st[:-1])) else 1
+        return self._permute(t, st, dims, vec, False), list(rows)
+
+    # ---- node execution ----------------------------------------------------------------------
+    def run(self, inputs: Dict[Tuple[str, object], torch.Tensor], B: int, nb: int, with_adjoint: bool,
+            seed=None):
+        """inputs: real-view fp32 tensors per input key (batched ones with the sample dimension
+        first, nsamples = B * nb).  Returns (values dict, layouts dict)."""
+        g = self.g
+        NS = B * nb
+        val: Dict[int, torch.Tensor] = {}
+        lay: Dict[int, List[int]] = {}
+
+        def get(n: Node):
+            return val[n.id], lay[n.id]
+
+        for n in g.nodes:
+            if n.role == "adj" and not with_adjoint:
+                continue
+            if n.kind == "input":
+                key = (n.operand.kind, n.operand.key)
+                if key[0] == "gradseed":     # d loss / d result: a tensor, or a callable of the forward result
+                    t = seed(val[g.result], lay[g.result]) if callable(seed) else seed
+                else:
+                    t = inputs[key]
+                val[n.id] = t
+                lay[n.id] = ([BATCH] if n.batched else []) + list(n.idx)
+                continue
+            if n.is_accum:
+                val[n.id] = torch.zeros(tuple(g.dims[i] for i in n.idx) or (1,), dtype=torch.float32, device=self.device)
+                lay[n.id] = list(n.idx)
+                continue
+            if n.kind == "seed":
+                raise NotImplementedError("fused loss is not part of the GEMM path (autograd route only)")
+            if n.kind == "lin":
+                out, out_layout = self._lin(n, val, lay, NS)
+            else:
+                out, out_layout = self._contract(n, val, lay, NS)
+            if n.acc_into >= 0:
+                # a contribution is declared in the target's memory order (its own labels: a core's
+                # L and R occurrences carry different index ids over the same buffer)
+                tgt = val[n.acc_into]
+                if out_layout != list(n.idx):
+                    out, _ = self._arrange(out, out_layout, list(n.idx), [], NS, exact=True)
+                tgt.add_(out.reshape(tgt.shape))
+            else:
+                val[n.id], lay[n.id] = out, out_layout
+        return val, lay
+
+    def _lin(self, n: Node, val, lay, NS):
+        g = self.g
+        src = g.nodes[n.p]
+        t, L = val[src.id], lay[src.id]
+        lead = [BATCH] if n.batched else []
+        strides, s = {}, 1
+        for i in reversed(L):
+            strides[i] = s
+            s *= self._extent(i, NS)
+        if n.lin_kind in ("permute", "conj"):
+            target = lead + list(n.idx)
+            dims = [self._extent(i, NS) for i in target]
+            st = [strides[i] for i in target]
+            conj = n.lin_kind == "conj"
+            if conj and not (L and L[-1] == src.idx[-1] and target[-1] == n.idx[-1]):
+                raise NotImplementedError("conjugation expects (re, im) innermost")
+            vec = 2 if (dims[-1] == 2 and st[-1] == 1 and len(dims) > 1) else 1
+            if conj and vec != 2:
+                raise NotImplementedError("conjugation expects interleaved complex data")
+            return self._permute(t, st, dims, vec, conj), target
+        if n.lin_kind == "expand":
+            ri, ro = n.idx[-2], n.idx[-1]
+            if strides[src.idx[-1]] != 1:      # (re, im) must be adjacent in the source
+                t, _ = self._arrange(t, L, [i for i in L if i != src.idx[-1]], [src.idx[-1]], NS)
+                L = [i for i in L if i != src.idx[-1]] + [src.idx[-1]]
+                strides, s = {}, 1
+                for i in reversed(L):
+                    strides[i] = s
+                    s *= self._extent(i, NS)
+            target = lead + list(n.idx)
+            dims = [self._extent(i, NS) for i in target]
+            st = [0 if i in (ri, ro) else strides[i] for i in target]
+            out = torch.empty(tuple(dims), dtype=torch.float32, device=self.device)
+            k = len(dims)
+            _lib.check(self.lib.tnq_cplx_expand_f32(c_void_p(t.data_ptr()), c_void_p(out.data_ptr()), k,
+                                                    (c_int64 * k)(*dims), (c_int64 * k)(*st), k - 2, k - 1, 0,
+                                                    self._stream()))
+            return out, target
+        if n.lin_kind == "fold":
+            # source: gradient of the expanded tensor, layout contains ri, ro somewhere
+            ri, ro = src.idx[-2], src.idx[-1]
+            target = lead + list(n.idx)
+            dims = [self._extent(i, NS) for i in target]
+            st = [strides[i] for i in target[:-1]] + [0]
+            out = torch.empty(tuple(dims), dtype=torch.float32, device=self.device)
+            k = len(dims)
+            _lib.check(self.lib.tnq_cplx_fold_f32(c_void_p(t.data_ptr()), c_void_p(out.data_ptr()), k,
+                                                  (c_int64 * k)(*dims), (c_int64 * k)(*st), strides[ri], strides[ro],
+                                                  0, 0, self._stream()))
+            return out, target
+        raise NotImplementedError(f"lin kind {n.lin_kind!r} in the GEMM path")
+
+    def _contract(self, n: Node, val, lay, NS):
+        g = self.g
+        p, q = g.nodes[n.p], g.nodes[n.q]
+        tp, Lp = val[p.id], lay[p.id]
+        tq, Lq = val[q.id], lay[q.id]
+        shared = [i for i in p.idx if i in q.idx]
+        pf = [i for i in p.idx if i not in shared]
+        qf = [i for i in q.idx if i not in shared]
+        if n.reduce_batch:
+            # gradient of a shared tensor: the sample index joins the contracted indices (GEMM K)
+            korder = self._tail_order(Lp, [BATCH] + shared)
+            A, rows_a = self._arrange(tp, Lp, pf, korder, NS)
+            Bm, rows_b = self._arrange(tq, Lq, qf, korder, NS)
+            M, N, K = self._size(pf, NS), self._size(qf, NS), self._size(korder, NS)
+            C = torch.empty((M, N), dtype=torch.float32, device=self.device)
+            self._gemm(A, Bm, C, M, N, K, K, K, N)
+            out_layout = rows_a + rows_b
+            return C.reshape([g.dims[i] for i in out_layout] or [1]), out_layout
+        if q.batched and not p.batched:   # the batched operand provides the GEMM rows
+            p, q, tp, Lp, tq, Lq, pf, qf = q, p, tq, Lq, tp, Lp, qf, pf
+        lead = [BATCH] if p.batched else []
+        korder = self._tail_order(Lp, shared)
+        A, rows_a = self._arrange(tp, Lp, lead + pf, korder, NS)
+        K = self._size(shared, NS)
+        if q.batched:
+            # both per-sample: one GEMM per sample (batch in grid.z)
+            Bm, rows_b = self._arrange(tq, Lq, [BATCH] + qf, korder, NS)
+            assert rows_a[0] == BATCH and rows_b[0] == BATCH
+            M, N = self._size(rows_a[1:], NS), self._size(rows_b[1:], NS)
+            C = torch.empty((NS, M, N), dtype=torch.float32, device=self.device)
+            for b0 in range(0, NS, 32768):
+                nb_ = min(32768, NS - b0)
+                self._gemm(A[b0:] if b0 else A, Bm[b0:] if b0 else Bm, C[b0:] if b0 else C, M, N, K, K, K, N,
+                           batch=nb_, sA=M * K, sB=N * K, sC=M * N)
+            out_layout = [BATCH] + rows_a[1:] + rows_b[1:]
+        else:
+            Bm, rows_b = self._arrange(tq, Lq, qf, korder, NS)
+            M, N = self._size(rows_a, NS), self._size(rows_b, NS)
+            C = torch.empty((M, N), dtype=torch.float32, device=self.device)
+            self._gemm(A, Bm, C, M, N, K, K, K, N)
+            out_layout = rows_a + rows_b
+        return C.reshape([self._extent(i, NS) for i in out_layout] or [1]), out_layout
+
+    @staticmethod
+    def _tail_order(layout, kset):
+        """The contracted indices in the order they already have in `layout`."""
+        ks = set(kset)
+        return [i for i in layout if i in ks]

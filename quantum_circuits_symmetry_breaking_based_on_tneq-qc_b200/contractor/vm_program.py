@@ -282,7 +282,8 @@ def lower(g: CGraph, mode: str, dtype: str, nb: int = 1, emit_values: bool = Tru
             else:
                 src = (space[p.id], base[p.id], slot_of.get(p.id, -1)) if p.kind != "input" else (SP_GIN, 0, slot_of[p.id])
             dst, acc = dst_loc(n)
-            op = dict(kind="lin", acc=acc, dst=dst, src=src, count=g.size(n.idx), sf=n.src_flat, cf=n.coef)
+            sf_, cf_ = g.lin_tables(n)
+            op = dict(kind="lin", acc=acc, dst=dst, src=src, count=g.size(n.idx), sf=sf_, cf=cf_)
             if n.batched:
                 body_ops.append(op)
             elif n.role == "adj":

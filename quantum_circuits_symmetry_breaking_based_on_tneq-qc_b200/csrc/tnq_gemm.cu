@@ -107,21 +107,33 @@ __device__ __forceinline__ float tf32_hi(float v) {
 }
 
 // one 8-row x 4-chunk unit of a tile: global (row, chunk) -> hi / lo tiles in canonical layout
+template <bool ALIGNED>
 __device__ __forceinline__ void stage_unit(const float* __restrict__ src, long long ld, long long rows_left,
                                            long long k_left, int unit, int lane, uint32_t hi_base, uint32_t lo_base) {
     const int rg = unit >> 1, half = unit & 1;
     const int r8 = lane & 7, c4 = lane >> 3;
     const int row = rg * 8 + r8, chunk = half * 4 + c4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < rows_left && chunk * 4 < k_left) v = __ldg(reinterpret_cast<const float4*>(src + row * ld + chunk * 4));
+    if (ALIGNED) {
+        if (row < rows_left && chunk * 4 < k_left) v = __ldg(reinterpret_cast<const float4*>(src + row * ld + chunk * 4));
+    } else if (row < rows_left) {   // odd K / leading dimension / base address: guarded scalar loads
+        const float* r = src + row * ld + chunk * 4;
+        const long long left = k_left - chunk * 4;
+        if (left > 0) v.x = __ldg(r);
+        if (left > 1) v.y = __ldg(r + 1);
+        if (left > 2) v.z = __ldg(r + 2);
+        if (left > 3) v.w = __ldg(r + 3);
+    }
     float4 h, l;
     h.x = tf32_hi(v.x), h.y = tf32_hi(v.y), h.z = tf32_hi(v.z), h.w = tf32_hi(v.w);
-    l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+    // lo is rounded to nearest TF32 as well: the tensor core would otherwise truncate it (biased)
+    l.x = tf32_hi(v.x - h.x), l.y = tf32_hi(v.y - h.y), l.z = tf32_hi(v.z - h.z), l.w = tf32_hi(v.w - h.w);
     const uint32_t off = (uint32_t)(rg * 64 + chunk * 8 + r8) * 16u;
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_base + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_base + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
 }
 
+template <bool ALIGNED>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, long long M,
                        long long N, long long K, long long lda, long long ldb, long long ldc, long long strideA,
@@ -167,8 +179,8 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int unit = warp * 8 + i;
-                stage_unit(A + k0, lda, M - m0, K - k0, unit, lane, st, st + TILE_BYTES);
-                stage_unit(B + k0, ldb, N - n0, K - k0, unit, lane, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
+                stage_unit<ALIGNED>(A + k0, lda, M - m0, K - k0, unit, lane, st, st + TILE_BYTES);
+                stage_unit<ALIGNED>(B + k0, ldb, N - n0, K - k0, unit, lane, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
             mbar_arrive(full0 + 8 * s);
@@ -240,16 +252,16 @@ extern "C" int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t
                                int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB,
                                int64_t strideC, int accumulate, void* stream) {
     if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || batch <= 0) return tnq_internal_fail("tnq_gemm_tf32x3: bad arguments");
-    if ((K & 3) || (lda & 3) || (ldb & 3) || (strideA & 3) || (strideB & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15))
-        return tnq_internal_fail("tnq_gemm_tf32x3: K, lda, ldb, batch strides must be multiples of 4 floats and A, B "
-                                 "16-byte aligned");
+    const bool aligned = !((K & 3) || (lda & 3) || (ldb & 3) || (strideA & 3) || (strideB & 3) || ((uintptr_t)A & 15) ||
+                           ((uintptr_t)B & 15));
     if (batch > 65535) return tnq_internal_fail("tnq_gemm_tf32x3: batch too large for one launch (max 65535)");
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-    cudaError_t e = cudaFuncSetAttribute(tnq_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = aligned ? tnq_gemm_tf32x3_kernel<true> : tnq_gemm_tf32x3_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(gemm)");
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
-    tnq_gemm_tf32x3_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(A, B, C, M, N, K, lda, ldb, ldc, strideA,
-                                                                                 strideB, strideC, accumulate);
+    kern<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC,
+                                                             accumulate);
     tnq_internal_count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_gemm_tf32x3 launch");

@@ -60,8 +60,13 @@ def test_gemm_shared_operand_strides_and_accumulate(built_lib):
     assert ((C.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
 
 
-def test_gemm_rejects_unaligned(built_lib):
-    A = torch.randn(8, 6, device="cuda")
-    B = torch.randn(8, 6, device="cuda")
-    with pytest.raises(RuntimeError, match="multiples of 4"):
-        _gemm(A, B)
+def test_gemm_unaligned_shapes(built_lib):
+    """Odd K / leading dimensions (outer products, K = 1) go through the guarded scalar loader."""
+    torch.manual_seed(9)
+    for M, N, K in [(8, 6, 6), (1, 16, 1), (50, 3, 7), (130, 129, 33)]:
+        A = torch.randn(2, M, K, device="cuda")
+        B = torch.randn(2, N, K, device="cuda")
+        C = _gemm(A, B)
+        torch.cuda.synchronize()
+        ref = A.double() @ B.double().transpose(-1, -2)
+        assert ((C.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5

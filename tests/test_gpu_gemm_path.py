@@ -1,0 +1,98 @@
+"""The large-bond-dimension route (permute kernels + tcgen05 3xTF32 GEMM) against the oracle.
+
+TNQ_FORCE_GEMM_PATH=1 sends small networks down the same route that bond dimension 64-128 takes,
+so that the CPU oracle can still check every number."""
+import os
+
+import pytest
+import torch
+
+import tneq_b200
+from oracle import qctn_oracle as oc
+from helpers import well_conditioned_case, upcast, clone_mx, rel_err
+
+pytestmark = pytest.mark.gpu
+H = tneq_b200.QCTNHelper
+
+
+def _to_dev(x, dev):
+    if isinstance(x, oc.TNT):
+        return tneq_b200.TNTensor(x.tensor.to(dev), x.scale, x.log_scale)
+    return x.to(dev)
+
+
+@pytest.fixture
+def force_gemm_path():
+    os.environ["TNQ_FORCE_GEMM_PATH"] = "1"
+    yield
+    os.environ.pop("TNQ_FORCE_GEMM_PATH", None)
+
+
+@pytest.mark.parametrize("kind,n,K,B,dtype", [("mps", 5, 4, 24, "float32"), ("mps", 4, 8, 10, "float32"),
+                                             ("mps", 5, 4, 12, "complex64"), ("mps", 4, 8, 6, "complex64"),
+                                             ("tree", 6, 4, 9, "float32"), ("mps", 3, 16, 5, "complex64")])
+def test_gemm_path_matches_oracle(kind, n, K, B, dtype, built_lib, force_gemm_path):
+    graph = H.generate_example_graph(n=n, graph_type=kind, dim_char=str(K))
+    names, table, nq, cores, states, mxs = well_conditioned_case(graph, K, B, dtype)
+    td64 = torch.complex128 if "complex" in dtype else torch.float64
+    want = oc.forward(graph, cores, states, clone_mx(mxs))
+    c64 = {k: v.to(td64) for k, v in cores.items()}
+    s64 = [s.to(td64) for s in states]
+    tl, tg = oc.loss_and_grads(graph, c64, s64, [upcast(m, td64) for m in clone_mx(mxs)])
+    wl, wg = oc.loss_and_grads(graph, cores, states, clone_mx(mxs))
+    be = tneq_b200.BackendFactory.create_backend("b200", device="cuda:0", dtype=dtype)
+    eng = tneq_b200.EngineSiamese(backend=be, strategy_mode="balanced", mx_K=K)
+    dev = torch.device("cuda:0")
+    q = tneq_b200.QCTN(graph, backend=be)
+    for k, v in cores.items():
+        q.cores_weights[k] = v.to(dev).requires_grad_(True)
+    st = [s.to(dev) for s in states]
+    launches0 = tneq_b200._lib.launch_count()
+    got = eng.contract_with_compiled_strategy(q, st, [_to_dev(m, dev) for m in clone_mx(mxs)])
+    fn = eng._compiled(q, st, [_to_dev(m, dev) for m in clone_mx(mxs)], True, "symmetric")
+    assert next(iter(fn.plans.values())).use_gemm_path and tneq_b200._lib.launch_count() > launches0
+    assert got.shape == want.shape
+    # complex dtypes return |amplitude|^2 (reference quirk D10): the amplitude's 1e-5 bound doubles
+    truth = oc.forward(graph, c64, s64, [upcast(m, td64) for m in clone_mx(mxs)])
+    tol_p = 2e-5 if "complex" in dtype else 1e-5
+    assert rel_err(got.double(), truth) < max(tol_p, 3 * rel_err(want.double(), truth))
+    for fused in (True, False):
+        loss, grads = eng.contract_with_compiled_strategy_for_gradient(
+            q, st, [_to_dev(m, dev) for m in clone_mx(mxs)], fused=fused)
+        assert abs(loss.item() - wl.item()) <= 1e-5 * abs(wl.item())
+        for g_, w, t in zip(grads, wg, tg):
+            assert g_.shape == w.shape and g_.dtype == w.dtype
+            ref_err = rel_err(w.to(td64), t)
+            assert rel_err(g_.to(td64), t) < max(1e-5, 3 * ref_err), (fused, rel_err(g_.to(td64), t), ref_err)
+
+
+def test_permute_kernel_paths(built_lib):
+    """direct and tiled code paths of tnq_permute_f32, real and complex (vec = 2), against torch."""
+    import ctypes
+    from ctypes import c_int64, c_void_p
+    from tneq_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    cases = [((6, 40, 50), (2, 1, 0), 1), ((3, 33, 65, 2), (2, 0, 1, 3), 2), ((64, 64, 64), (1, 2, 0), 1),
+             ((5, 7, 9, 4), (0, 2, 1, 3), 4), ((130, 70), (1, 0), 1), ((8, 3, 3, 2), (0, 2, 1, 3), 2)]
+    for shape, perm, vec in cases:
+        x = torch.randn(*shape, device="cuda")
+        want = x.permute(*perm).contiguous()
+        out = torch.empty_like(want)
+        dims = list(want.shape)
+        st = [x.stride(p) for p in perm]
+        n = len(dims)
+        _lib.check(lib.tnq_permute_f32(c_void_p(x.data_ptr()), c_void_p(out.data_ptr()), n, (c_int64 * n)(*dims),
+                                       (c_int64 * n)(*st), vec, 0, c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        assert torch.equal(out, want), (shape, perm, vec)
+    # conjugation rides along for interleaved complex data
+    z = torch.randn(9, 11, 5, dtype=torch.complex64, device="cuda")
+    x = torch.view_as_real(z)
+    want = torch.view_as_real(z.permute(2, 0, 1).conj().resolve_conj().contiguous())
+    out = torch.empty_like(want)
+    dims, st = list(want.shape), [x.stride(2), x.stride(0), x.stride(1), 1]
+    _lib.check(lib.tnq_permute_f32(c_void_p(x.data_ptr()), c_void_p(out.data_ptr()), 4, (c_int64 * 4)(*dims),
+                                   (c_int64 * 4)(*st), 2, 1, c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
