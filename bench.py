@@ -43,6 +43,10 @@ WORKLOADS = {
                  name="cfg3: 24-qubit 2-layer merged MPS QCTN, K=3, fwd+loss+bwd, global batch 16384"),
     "cfg3-fwd": dict(kind="merged", n=24, K=3, batch=16384, mode="fwd", dtype="float32",
                      name="24-qubit 2-layer merged MPS QCTN, K=3, forward only, batch 16384"),
+    "cfg4": dict(kind="mps", n=16, K=64, batch=256, mode="train", dtype="complex64", weak=True, near_identity=True,
+                 name="cfg4: 16-qubit MPS QCTN, bond 64, complex64, fwd+loss+bwd, batch 256 per GPU (tcgen05 GEMM path)"),
+    "cfg4-32": dict(kind="mps", n=16, K=32, batch=256, mode="train", dtype="complex64", weak=True, near_identity=True,
+                    name="16-qubit MPS QCTN, bond 32, complex64, fwd+loss+bwd, batch 256 per GPU (tcgen05 GEMM path)"),
     "cfg2": dict(kind="mps", n=16, K=3, batch=4096, mode="fwd", dtype="float32",
                  name="cfg2: 16-qubit MPS QCTN, K=3, forward probabilities, batch 4096"),
     "cfg2-large": dict(kind="mps", n=16, K=3, batch=1 << 20, mode="fwd", dtype="float32",
@@ -129,14 +133,21 @@ def time_reference(args, wl):
     from oracle import qctn_oracle as oc
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
+    wl = dict(wl)
+    note = ""
+    if wl["K"] > 8:
+        # left-to-right einsum keeps B*K^6 intermediates: infeasible on a CPU at bond 64; the largest
+        # bond that runs in bounded time is used and said so
+        note = f" [bond reduced from {wl['K']} to 8: the reference's B*K^6 intermediates do not fit at bond {wl['K']}]"
+        wl["K"] = 8
     graph = build_graph(tb, wl["kind"], wl["n"], wl["K"])
     names, table, nq, cores, x_all = synth_inputs(graph, wl["K"], 4096, wl["dtype"])
-    states = oc.unit_states(nq, wl["K"])
+    states = oc.unit_states(nq, wl["K"], getattr(torch, wl["dtype"]))
     n_steps = args.steps if args.impl == "reference" else 3
     n_warm = max(1, args.warmup) if args.impl == "reference" else 1
 
     def run_once(xb):
-        mx, _ = oc.generate_data(xb, wl["K"], torch.float32, "TNTensor")  # fresh: auto_scale is in place
+        mx, _ = oc.generate_data(xb, wl["K"], getattr(torch, wl["dtype"]), "TNTensor")  # fresh: auto_scale is in place
         t0 = time.perf_counter()
         if wl["mode"] == "train":
             oc.loss_and_grads(graph, cores, states, mx)
@@ -167,7 +178,7 @@ def time_reference(args, wl):
     val = sample_b * len(times) / total
     return dict(value=val, unit="samples/s", cores=threads, kind="port",
                 sample=f"{len(times)} steps of batch {sample_b} of the same network ({wl['mode']}), "
-                       f"oracle port of the reference CPU path (bit-identical to /root/reference on CPU)",
+                       f"oracle port of the reference CPU path (bit-identical to /root/reference on CPU)" + note,
                 ms_per_step=1e3 * total / len(times), batch=sample_b)
 
 
@@ -224,27 +235,53 @@ def main():
     torch.cuda.set_device(dev)
 
     K, n = wl["K"], wl["n"]
+    esz = 8 if "complex" in wl["dtype"] else 4
     graph = build_graph(tb, wl["kind"], n, K)
-    B_global = wl["batch"]
-    B = B_global // world                      # strong scaling: the global batch is fixed
-    names, table, nq, cores_cpu, x_cpu = synth_inputs(graph, K, B_global, wl["dtype"])
+    weak = bool(wl.get("weak"))
+    B_global = wl["batch"] * world if weak else wl["batch"]
+    B = B_global // world                      # strong scaling: global batch fixed; weak: per-GPU batch fixed
+    big = K >= 16
+    if big:                                    # 64^4 cores: QR-orthogonal init on the device (seeded)
+        from oracle import qctn_oracle as oc
+        names, table, nq = oc.parse_graph(graph)
+        torch.manual_seed(1234)
+        tdt = getattr(torch, wl["dtype"])
+        cores_cpu = {}
+        for c in names:
+            m = torch.randn(K * K, K * K, dtype=tdt, device=f"cuda:{local_rank}")
+            qm, rm = torch.linalg.qr(m)
+            d = torch.diagonal(rm)
+            cores_cpu[c] = (qm * (d / d.abs()).conj().unsqueeze(0)).reshape(K, K, K, K)
+        torch.manual_seed(42)
+        x_cpu = torch.randn(B_global, nq)
+    else:
+        names, table, nq, cores_cpu, x_cpu = synth_inputs(graph, K, B_global, wl["dtype"])
     x_local = x_cpu[rank * B:(rank + 1) * B]
 
     backend = tb.BackendFactory.create_backend("b200", device=str(dev), dtype=wl["dtype"])
     engine = tb.EngineSiamese(backend=backend, strategy_mode="balanced", mx_K=K)
     qctn = tb.QCTN(graph, backend=backend)
-    packed = torch.cat([cores_cpu[c].reshape(-1) for c in names]).to(dev)
-    if dist is not None:
-        dist.broadcast(packed, src=0)          # the reference forgets this
-    off = 0
     for c in names:
-        cnt = cores_cpu[c].numel()
-        qctn.cores_weights[c] = packed[off:off + cnt].reshape(cores_cpu[c].shape).clone().requires_grad_(True)
-        off += cnt
-    states = [torch.zeros(K, device=dev) for _ in range(nq)]
+        w = cores_cpu[c].to(dev).clone()
+        if dist is not None:                   # the reference forgets this
+            dist.broadcast(torch.view_as_real(w) if w.is_complex() else w, src=0)
+        qctn.cores_weights[c] = w.requires_grad_(True)
+    tdt = getattr(torch, wl["dtype"])
+    states = [torch.zeros(K, device=dev, dtype=tdt) for _ in range(nq)]
     for s in states:
         s[-1] = 1.0
-    mx_dev, _ = engine.generate_data(x_local.to(dev), K=K, ret_type="TNTensor")
+    if wl.get("near_identity"):
+        # large bond: a random unitary's overlap with a product state is ~K^-n, far below the loss's
+        # 1e-10 clamp for ANY projector data; measurement matrices I + 0.1 H (H random
+        # Hermitian, unit spectral scale) keep the value O(1) so that loss and gradients are live
+        torch.manual_seed(42 + rank)
+        mx_dev = []
+        for _ in range(nq):
+            h = torch.randn(B, K, K, dtype=tdt, device=dev) / (2.0 * K ** 0.5)
+            m = torch.eye(K, dtype=tdt, device=dev) + 0.1 * (h + h.transpose(1, 2).conj())
+            mx_dev.append(tb.TNTensor(m))
+    else:
+        mx_dev, _ = engine.generate_data(x_local.to(dev), K=K, ret_type="TNTensor")
     log_scale = sum(m.log_scale for m in mx_dev)
     mx_dev = [tb.TNTensor(m.tensor.contiguous(), m.scale, m.log_scale) for m in mx_dev]
     mx_host = [m.tensor.cpu().pin_memory() for m in mx_dev]
@@ -327,11 +364,20 @@ def main():
 
     # roofline of the dominant kernel (tnq_body_kernel): measured alone with CUDA events
     bound = next(iter(fn.plans.values()))
-    prog = bound.program("train" if train else "fwd")
-    info = prog.info(B * bound.plan.nb)
-    flops_launch = prog.prog.flops_per_sample * B * bound.plan.nb
-    mx_bytes = B * nq * K * K * 4
-    core_bytes = sum(v.numel() * 4 for v in cores_cpu.values())
+    gemm_path = bound.use_gemm_path
+    if gemm_path:
+        runner = bound.gemm_runner("bwd" if train else "fwd")
+        f0 = runner.flops
+        step_device()
+        torch.cuda.synchronize(dev)
+        flops_launch = runner.flops - f0           # real fp32-equivalent flops of all GEMMs of one step
+        info = None
+    else:
+        prog = bound.program("train" if train else "fwd")
+        info = prog.info(B * bound.plan.nb)
+        flops_launch = prog.prog.flops_per_sample * B * bound.plan.nb
+    mx_bytes = B * nq * K * K * esz
+    core_bytes = sum(v.numel() * esz for v in cores_cpu.values())
     alg_bytes = mx_bytes + B * 4 + core_bytes * (2 if train else 1)
     peaks = {}
     try:
@@ -356,14 +402,26 @@ def main():
     del a, b
     kernel_ms = ms_step  # the body kernel is >95% of the step (profiles/ ncu launch list)
     achieved_tf = flops_launch / (kernel_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp32_peak, "traffic": None,
-                "peak_source": "measured here: torch.matmul 8192^3 fp32 (TF32 off), best of 5",
-                "kernel": "tnq_body_kernel", "flops_per_launch": flops_launch,
-                "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9,
-                        "peak_gbs": peaks.get("hbm_gbs"), "source": "MEASURED_PEAKS.json (measured)" if peaks else None},
-                "tile_samples": info.tile_samples, "grid": info.grid, "frame_in_smem": bool(info.frame_in_smem),
-                "smem_bytes": info.smem_bytes}
+    hbm = {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9,
+           "peak_gbs": peaks.get("hbm_gbs"), "source": "MEASURED_PEAKS.json (measured)" if peaks else None}
+    if gemm_path:
+        # tensor-core roofline: fp32-equivalent flops; 3xTF32 issues 3 TF32 MMAs per product and dense TF32
+        # runs at half the bf16 rate, so the fp32-equivalent peak is bf16_measured / 2 / 3
+        bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
+        tc_peak = bf16 / 2.0 / 3.0
+        roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": tc_peak, "unit": "TFLOP/s",
+                    "frac": achieved_tf / tc_peak, "traffic": None,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1590")
+                                   + " / 2 (TF32 rate) / 3 (3xTF32 passes); whole step incl. permutes",
+                    "kernel": "tnq_gemm_tf32x3_kernel", "flops_per_launch": flops_launch,
+                    "issued_tf32_tflops": 3 * achieved_tf, "fp32_simt_peak_measured": fp32_peak, "hbm": hbm}
+    else:
+        roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": achieved_tf / fp32_peak, "traffic": None,
+                    "peak_source": "measured here: torch.matmul 8192^3 fp32 (TF32 off), best of 5",
+                    "kernel": "tnq_body_kernel", "flops_per_launch": flops_launch, "hbm": hbm,
+                    "tile_samples": info.tile_samples, "grid": info.grid, "frame_in_smem": bool(info.frame_in_smem),
+                    "smem_bytes": info.smem_bytes}
 
     line = {"metric": "samples/sec for QCTN fwd+bwd contraction" if train else "samples/sec for QCTN forward contraction",
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

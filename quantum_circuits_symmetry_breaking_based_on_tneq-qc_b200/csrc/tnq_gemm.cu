@@ -10,14 +10,16 @@
 // torch.einsum per qubit group) is a real GEMM: rows = batch x kept indices, K = contracted
 // indices.  Complex contractions arrive here as real GEMMs of doubled K and N (2x2-real form).
 //
-// Kernel anatomy (one 128 x 128 output tile per CTA, 160 threads):
-//   warps 0-3  producers : 16-byte global loads of the fp32 A / B tiles, split into TF32 hi and
-//                          lo, stored to shared memory directly in the UMMA canonical K-major
-//                          layout (8-row x 16-byte core matrices, no swizzle), 3-stage ring,
-//                          fence.proxy.async + mbarrier arrive;
+// Kernel anatomy (one 128 x 128 output tile per CTA, 288 threads):
+//   warps 0-7  producers : 16-byte global loads of the fp32 A / B tiles (all loads of a stage are
+//                          issued before any is consumed), split into TF32 hi and lo, stored to
+//                          shared memory directly in the UMMA canonical K-major layout (8-row x
+//                          16-byte core matrices, no swizzle), 3-stage ring, fence.proxy.async +
+//                          mbarrier arrive;
 //                          afterwards the epilogue: tcgen05.ld 32 lanes x 32 columns -> registers
-//                          -> 128-byte row segments in global memory;
-//   warp 4     MMA issuer: one elected lane waits on the stage's "full" mbarrier and issues
+//                          -> 32x33 shared-memory transpose -> one coalesced 128-byte row segment
+//                          per store instruction;
+//   warp 8     MMA issuer: one elected lane waits on the stage's "full" mbarrier and issues
 //                          4 k-steps x 3 tcgen05.mma (M=128, N=128, K=8), then tcgen05.commit to
 //                          the stage's "empty" mbarrier; owns the TMEM allocation (128 columns).
 #include <cuda_runtime.h>
@@ -37,7 +39,7 @@ constexpr int BM = 128, BN = 128, BK = 32;          // tile (BK floats = 128 byt
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB, one of {A hi, A lo, B hi, B lo}
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // 64 KB
-constexpr int PRODUCERS = 128;
+constexpr int PRODUCERS = 256;                      // 8 producer / epilogue warps
 constexpr int GEMM_THREADS = PRODUCERS + 32;
 constexpr uint32_t TMEM_COLS = 128;
 
@@ -106,10 +108,10 @@ __device__ __forceinline__ float tf32_hi(float v) {
     return __uint_as_float(r);
 }
 
-// one 8-row x 4-chunk unit of a tile: global (row, chunk) -> hi / lo tiles in canonical layout
+// one 8-row x 4-chunk unit of a tile: global (row, chunk) -> register
 template <bool ALIGNED>
-__device__ __forceinline__ void stage_unit(const float* __restrict__ src, long long ld, long long rows_left,
-                                           long long k_left, int unit, int lane, uint32_t hi_base, uint32_t lo_base) {
+__device__ __forceinline__ float4 load_unit(const float* __restrict__ src, long long ld, long long rows_left,
+                                            long long k_left, int unit, int lane) {
     const int rg = unit >> 1, half = unit & 1;
     const int r8 = lane & 7, c4 = lane >> 3;
     const int row = rg * 8 + r8, chunk = half * 4 + c4;
@@ -124,6 +126,14 @@ __device__ __forceinline__ void stage_unit(const float* __restrict__ src, long l
         if (left > 2) v.z = __ldg(r + 2);
         if (left > 3) v.w = __ldg(r + 3);
     }
+    return v;
+}
+
+// register -> TF32 hi / lo tiles in the canonical layout
+__device__ __forceinline__ void store_unit(float4 v, int unit, int lane, uint32_t hi_base, uint32_t lo_base) {
+    const int rg = unit >> 1, half = unit & 1;
+    const int r8 = lane & 7, c4 = lane >> 3;
+    const int chunk = half * 4 + c4;
     float4 h, l;
     h.x = tf32_hi(v.x), h.y = tf32_hi(v.y), h.z = tf32_hi(v.z), h.w = tf32_hi(v.w);
     // lo is rounded to nearest TF32 as well: the tensor core would otherwise truncate it (biased)
@@ -156,7 +166,7 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == PRODUCERS / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
                      "r"(TMEM_COLS)
                      : "memory");
@@ -168,7 +178,7 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
     const uint32_t tmem_base = tmem_base_slot;
     const int nkb = (int)((K + BK - 1) / BK);
 
-    if (warp < 4) {
+    if (warp < PRODUCERS / 32) {
         // ---------------- producers ----------------
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
@@ -176,24 +186,32 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
             mbar_wait(empty0 + 8 * s, phase ^ 1u);
             const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
             const long long k0 = (long long)kb * BK;
+            float4 va[4], vb[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int unit = warp * 8 + i;
-                stage_unit<ALIGNED>(A + k0, lda, M - m0, K - k0, unit, lane, st, st + TILE_BYTES);
-                stage_unit<ALIGNED>(B + k0, ldb, N - n0, K - k0, unit, lane, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
+            for (int i = 0; i < 4; ++i) {        // all global loads of the stage first ...
+                va[i] = load_unit<ALIGNED>(A + k0, lda, M - m0, K - k0, warp * 4 + i, lane);
+                vb[i] = load_unit<ALIGNED>(B + k0, ldb, N - n0, K - k0, warp * 4 + i, lane);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {        // ... then split and store
+                store_unit(va[i], warp * 4 + i, lane, st, st + TILE_BYTES);
+                store_unit(vb[i], warp * 4 + i, lane, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
             mbar_arrive(full0 + 8 * s);
         }
         // ---------------- epilogue ----------------
+        // warp w reads TMEM lanes [32 (w % 4), +32) (hardware rule) and the column half w / 4
         mbar_wait(accum_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const long long row = m0 + warp * 32 + lane;
-        float* crow = C + row * ldc + n0;
+        const int quad = warp & 3, chalf = warp >> 2;
+        float* xpose = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // pipeline smem is idle now
+        const long long row0 = m0 + quad * 32;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c0 = chalf * 64 + cc * 32;
             uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -204,16 +222,21 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < M) {
+            // lane = row of the 32 x 32 block: transpose so that a store instruction covers one row
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const long long col = n0 + c0 + j;
-                    if (col < N) {
-                        const float v = __uint_as_float(r[j]);
-                        crow[c0 + j] = accumulate ? crow[c0 + j] + v : v;
-                    }
+            for (int j = 0; j < 32; ++j) xpose[lane * 33 + j] = __uint_as_float(r[j]);
+            __syncwarp();
+            const long long col = n0 + c0 + lane;
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+                const long long row = row0 + rr;
+                if (row < M && col < N) {
+                    float* d = C + row * ldc + col;
+                    const float v = xpose[rr * 33 + lane];
+                    *d = accumulate ? *d + v : v;
                 }
             }
+            __syncwarp();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
@@ -241,7 +264,7 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
         }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == PRODUCERS / 32) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
