@@ -208,7 +208,8 @@ def main():
         ref = time_reference(args, wl)
         line = {"impl": "reference", "metric": "samples/sec for QCTN fwd+bwd contraction", "value": ref["value"],
                 "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ref["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "ms_per_step": ref["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak" if wl.get("weak") else "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["name"], "reference_sample_batch": ref["batch"]},
                 "cpu_baseline": {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -425,8 +426,9 @@ def main():
 
     line = {"metric": "samples/sec for QCTN fwd+bwd contraction" if train else "samples/sec for QCTN forward contraction",
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if weak else "strong",
+            "vs_baseline": None,
+            "dtype": "f32" if esz == 4 else "c64 (real fp32 arithmetic: 3xTF32 on tcgen05)", "data": "synthetic",
             "config": {"workload": wl["name"], "global_batch": B_global, "per_gpu_batch": B, "qubits": nq, "K": K,
                        "cores": len(names), "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": f"batch sharded over {world} GPU(s); cores replicated; "
