@@ -96,9 +96,15 @@ class GemmPathRunner:
         NS = B * nb
         val: Dict[int, torch.Tensor] = {}
         lay: Dict[int, List[int]] = {}
-
-        def get(n: Node):
-            return val[n.id], lay[n.id]
+        # look-ahead: the indices a node's consumer will contract (so the producer can emit them
+        # innermost and the consumer needs no permute of the big tensor)
+        self._knext = {}
+        for m in g.nodes:
+            if m.kind == "contract" and (with_adjoint or m.role != "adj"):
+                p_, q_ = g.nodes[m.p], g.nodes[m.q]
+                sh = set(p_.idx) & set(q_.idx)
+                self._knext.setdefault(p_.id, sh)
+                self._knext.setdefault(q_.id, sh)
 
         for n in g.nodes:
             if n.role == "adj" and not with_adjoint:
@@ -221,7 +227,11 @@ class GemmPathRunner:
                            batch=nb_, sA=M * K, sB=N * K, sC=M * N)
             out_layout = [BATCH] + rows_a[1:] + rows_b[1:]
         else:
-            Bm, rows_b = self._arrange(tq, Lq, qf, korder, NS)
+            # order B's kept indices so that what the consumer contracts next ends up innermost in C
+            kn = self._knext.get(n.id, set())
+            want_b = [i for i in qf if i not in kn] + [i for i in qf if i in kn]
+            cur_b = [i for i in Lq if i in set(qf)]
+            Bm, rows_b = self._arrange(tq, Lq, want_b, korder, NS, exact=(want_b != cur_b))
             M, N = self._size(rows_a, NS), self._size(rows_b, NS)
             C = torch.empty((M, N), dtype=torch.float32, device=self.device)
             self._gemm(A, Bm, C, M, N, K, K, K, N)

@@ -41,7 +41,7 @@ constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB, one of {A hi, A lo
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // 64 KB
 constexpr int PRODUCERS = 256;                      // 8 producer / epilogue warps
 constexpr int GEMM_THREADS = PRODUCERS + 32;
-constexpr uint32_t TMEM_COLS = 128;
+constexpr uint32_t TMEM_COLS = 512;                 // 3 round-robin hi*hi accumulators + 1 for the correction terms
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -222,9 +222,28 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+#pragma unroll 1
+            for (int extra = 1; extra < 4; ++extra) {
+                if (extra < 3 && nkb * (BK / 8) <= extra) continue;   // that accumulator was never written
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr + (uint32_t)(extra * BN)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+            }
             // lane = row of the 32 x 32 block: transpose so that a store instruction covers one row
 #pragma unroll
-            for (int j = 0; j < 32; ++j) xpose[lane * 33 + j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) xpose[lane * 33 + j] = acc[j];
             __syncwarp();
             const long long col = n0 + c0 + lane;
 #pragma unroll 4
@@ -253,9 +272,17 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
                     const uint32_t ko = (uint32_t)j * 2u * 128u;     // two 16-byte chunks per K=8 step
                     const uint64_t a_hi = umma_desc(st + ko), a_lo = umma_desc(st + TILE_BYTES + ko);
                     const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES + ko), b_lo = umma_desc(st + 3 * TILE_BYTES + ko);
-                    umma_tf32(tmem_base, a_lo, b_hi, (kb | j) != 0);
-                    umma_tf32(tmem_base, a_hi, b_lo, 1u);
-                    umma_tf32(tmem_base, a_hi, b_hi, 1u);
+                    // The tensor core truncates (round-toward-zero) when it adds into the fp32
+                    // accumulator; every add costs ~1/2 ulp of the ACCUMULATOR.  The correction
+                    // terms are 2^-11 smaller, so they get their own accumulator (their truncation
+                    // errors are 2^-11 smaller too) and the two are summed once, round-to-nearest,
+                    // in the epilogue (Ootomo & Yokota's split-accumulator scheme).
+                    // The hi*hi products themselves are spread round-robin over three accumulators,
+                    // which cuts the length of every truncating chain by three.
+                    const int step = kb * (BK / 8) + j;
+                    umma_tf32(tmem_base + 3 * BN, a_lo, b_hi, step != 0);
+                    umma_tf32(tmem_base + 3 * BN, a_hi, b_lo, 1u);
+                    umma_tf32(tmem_base + (uint32_t)(step % 3) * BN, a_hi, b_hi, step >= 3);
                 }
                 umma_commit(empty0 + 8 * s);                          // frees the stage when the MMAs retire
                 if (kb == nkb - 1) umma_commit(accum_bar);            // accumulator complete

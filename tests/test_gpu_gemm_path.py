@@ -66,6 +66,32 @@ def test_gemm_path_matches_oracle(kind, n, K, B, dtype, built_lib, force_gemm_pa
             assert rel_err(g_.to(td64), t) < max(1e-5, 3 * ref_err), (fused, rel_err(g_.to(td64), t), ref_err)
 
 
+def test_large_bond_normalisation(built_lib):
+    """KAT-1 at a bond dimension the CPU oracle cannot reach (32, complex64): unitary cores (QR in
+    complex128, then cast) + identity measurements => value 1 for every sample.
+    Tolerance 5e-5, not 1e-5: the tensor core adds into its fp32 accumulator with truncation, which
+    leaves a systematic bias of roughly -1e-6 per GEMM in the chain even with the split-accumulator
+    scheme of tnq_gemm.cu (measured -3.2e-5 here, -6.7e-6 at bond 16); DESIGN.md section 4."""
+    K, n, B = 32, 6, 3
+    graph = H.generate_example_graph(n=n, graph_type="mps", dim_char=str(K))
+    be = tneq_b200.BackendFactory.create_backend("b200", device="cuda:0", dtype="complex64")
+    eng = tneq_b200.EngineSiamese(backend=be, strategy_mode="balanced", mx_K=K)
+    q = tneq_b200.QCTN(graph)
+    torch.manual_seed(0)
+    for c in q.cores:
+        m = torch.randn(K * K, K * K, dtype=torch.complex128, device="cuda")
+        qm, _ = torch.linalg.qr(m)
+        q.cores_weights[c] = qm.reshape(K, K, K, K).to(torch.complex64)
+    st = [torch.zeros(K, dtype=torch.complex64, device="cuda") for _ in range(n)]
+    for s in st:
+        s[-1] = 1.0
+    eye = torch.eye(K, dtype=torch.complex64, device="cuda").expand(B, K, K)
+    got = eng.contract_with_compiled_strategy(q, st, [eye] * n)
+    fn = eng._compiled(q, st, [eye] * n, True, "symmetric")
+    assert next(iter(fn.plans.values())).use_gemm_path
+    assert torch.allclose(got.cpu(), torch.ones(B), atol=5e-5), got
+
+
 def test_permute_kernel_paths(built_lib):
     """direct and tiled code paths of tnq_permute_f32, real and complex (vec = 2), against torch."""
     import ctypes
