@@ -31,6 +31,7 @@ extern "C" {
 
 #define TNQ_MAX_INPUTS 192
 #define TNQ_MAX_OUTPUTS 128
+#define TNQ_CHAIN_MAX_QUBITS 64
 
 typedef struct tnq_plan tnq_plan_t;
 
@@ -80,6 +81,20 @@ int tnq_plan_query(const tnq_plan_t* plan, int64_t nsamples, tnq_run_info_t* inf
 int tnq_plan_run(tnq_plan_t* plan, int64_t nsamples, const void* const* in_ptrs,
                  const int64_t* in_stride_hi, const int64_t* in_stride_lo, void* const* out_ptrs,
                  const double* scalars, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Register-resident sweep for single-layer MPS networks (the reference's default graph,
+ * QCTNHelper.generate_example_graph(graph_type="mps")), float32, edge rank K in {2,3,4}: the whole
+ * greedy sweep greedy_strategy.py:461-598 -- and for mode != 0 the loss engine_siamese.py:490-530 and
+ * the reverse sweep -- in one kernel with the K x K environment in registers.
+ *   cores[q]  q < n-1 : [K][K][K][K]   states[q] : [K]   mx[q] : sample b at mx[q] + b * mx_stride[q], [K][K]
+ *   mode 0: values[B]                       mode 1: values[B] (optional), *loss, grads[q] (fused loss)
+ *   mode 2: grads[q] seeded by seed[B] = d loss / d value (torch.autograd route)
+ */
+int64_t tnq_mps_chain_workspace_bytes(int K, int n, int64_t B);
+int tnq_mps_chain(int K, int n, const float* const* cores, const float* const* states, const float* const* mx,
+                  const int64_t* mx_stride, int64_t B, int mode, const float* seed, float* values, float* loss,
+                  float* const* grads, double log_scale, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Large-bond-dimension regime: one pairwise contraction of the sweep as a batched GEMM on the

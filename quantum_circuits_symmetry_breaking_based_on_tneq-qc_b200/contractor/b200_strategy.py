@@ -71,6 +71,8 @@ class _Bound:
         self._gemm: Dict[str, object] = {}
         biggest = max(int(torch.tensor(s).prod()) for s in plan.core_shapes.values()) * (2 if plan.complex_mode else 1)
         self.use_gemm_path = biggest > VM_MAX_CORE_ELEMS or os.environ.get("TNQ_FORCE_GEMM_PATH") == "1"
+        self.chain_rank = 0 if (self.use_gemm_path or os.environ.get("TNQ_NO_CHAIN") == "1") else plan.mps_chain_rank()
+        self._chain_ws = None
         if self.use_gemm_path and plan.real_dtype != "f32":
             raise NotImplementedError("large-bond contraction runs on the tensor cores in float32 / complex64 only; "
                                       f"got {plan.dtype} with a core of {biggest} elements")
@@ -150,6 +152,42 @@ class _Call:
             return torch.view_as_complex(flat.reshape(lead + body + [2]))
         return flat.reshape(lead + body)
 
+    # ---- single-layer MPS route: register-resident chain kernel (csrc/tnq_chain.cu) -----------
+    def _chain(self, cores, mode, seed=None, log_scale=0.0):
+        import ctypes
+        from ctypes import c_void_p, c_int64
+        from .. import _lib
+        lib = _lib.load()
+        K, n, dev = self.bound.chain_rank, self.bound.plan.nqubits, self.bound.device
+        by_key = dict(zip(self.core_keys, cores))
+        order = [k for k in self.bound.plan.core_shapes]                   # ('core', name) in qctn.cores order
+        cs = [by_key[k].detach().contiguous() for k in order]
+        sts = [self.states[q].detach().contiguous() for q in range(n)]
+        ms, strides = [], []
+        for q in range(n):
+            m = self.mxs[q].detach()
+            if m.stride(-1) != 1 or m.stride(-2) != K:
+                m = m.contiguous()
+            ms.append(m)
+            strides.append(0 if (m.shape[0] == 1 and self.B != 1) else m.stride(0))
+        ws_bytes = int(lib.tnq_mps_chain_workspace_bytes(K, n, self.B))
+        if self.bound._chain_ws is None or self.bound._chain_ws.numel() < ws_bytes:
+            self.bound._chain_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        values = torch.empty(self.B, dtype=torch.float32, device=dev) if mode != 2 else None
+        loss = torch.empty(1, dtype=torch.float32, device=dev) if mode == 1 else None
+        grads = [torch.empty_like(c) for c in cs] if mode != 0 else []
+        arr = lambda ts: (c_void_p * max(1, len(ts)))(*[t.data_ptr() for t in ts])
+        with torch.cuda.device(dev):
+            _lib.check(lib.tnq_mps_chain(K, n, arr(cs), arr(sts), arr(ms), (c_int64 * n)(*strides), self.B, mode,
+                                         c_void_p(seed.data_ptr()) if seed is not None else None,
+                                         c_void_p(values.data_ptr()) if values is not None else None,
+                                         c_void_p(loss.data_ptr()) if loss is not None else None,
+                                         arr(grads) if grads else None, float(log_scale),
+                                         c_void_p(self.bound._chain_ws.data_ptr()), self.bound._chain_ws.numel(),
+                                         c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        gmap = dict(zip(order, grads))
+        return values, (loss[0] if loss is not None else None), [gmap[k] for k in self.core_keys] if grads else []
+
     # ---- large-bond route: node-by-node on the tcgen05 GEMM path ------------------------------
     def _gemm_inputs(self, cores):
         out = {}
@@ -182,6 +220,8 @@ class _Call:
         return grads, val[r.g.result]
 
     def forward(self, cores):
+        if self.bound.chain_rank:
+            return self._chain(cores, 0)[0]
         if self.bound.use_gemm_path:
             return self._gemm_forward(cores)
         prog = self.bound.program("fwd")
@@ -189,6 +229,8 @@ class _Call:
         return self._shape_result(flat)
 
     def backward(self, cores, grad_out):
+        if self.bound.chain_rank:
+            return self._chain(cores, 2, seed=grad_out.reshape(-1).to(torch.float32).contiguous())[2]
         if self.bound.use_gemm_path:
             seed = _real_view(grad_out.contiguous()).reshape(self.nsamples, -1).to(torch.float32).contiguous()
             return self._gemm_backward(cores, seed)[0]
@@ -209,6 +251,9 @@ class _Call:
 
     def train(self, cores, log_scale: float):
         """Fused forward + loss + reverse sweep.  Returns (loss, grads, values)."""
+        if self.bound.chain_rank:
+            values, loss, grads = self._chain(cores, 1, log_scale=log_scale)
+            return loss, grads, values
         if self.bound.use_gemm_path:
             # forward nodes, then the loss seed from the forward result (element-wise, torch), then the
             # adjoint nodes -- one walk over the graph

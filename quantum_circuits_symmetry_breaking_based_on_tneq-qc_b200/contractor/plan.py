@@ -71,6 +71,27 @@ class ContractionPlan:
     def equations(self) -> List[str]:
         return self.schedule.equations
 
+    def mps_chain_rank(self) -> int:
+        """K if this is a single-layer MPS sweep that the register-resident chain kernel covers
+        (csrc/tnq_chain.cu): float32, every group of the canonical form, uniform edge rank 2..4,
+        plain (B,K,K) measurements on every qubit; else 0."""
+        n = self.nqubits
+        eq = self.schedule.equations
+        if self.dtype != "float32" or self.nb != 1 or n < 2 or n > 64 or len(eq) != n:
+            return 0
+        want = ["cdef,c,aeg,higj,h,d,i->ajf"] + ["cdef,aeg,higj,ahc,d,i->ajf"] * (n - 2) + ["acd,adc->a"]
+        if n == 2:
+            want = ["cdef,c,aeg,higj,h,d,i->ajf", "acd,adc->a"]
+        if eq != want or len(self.core_shapes) != n - 1 or any(k[0] != "core" for k in self.core_shapes):
+            return 0
+        ranks = {d for shp in self.core_shapes.values() for d in shp}
+        for st in self.schedule.steps:
+            ranks |= set(st.dims.values())
+        if len(ranks) != 1:
+            return 0
+        K = ranks.pop()
+        return K if 2 <= K <= 4 else 0
+
     def graph(self, mode: str) -> cgraph.CGraph:
         key = "fwd" if mode == "fwd" else mode
         if key not in self._graphs:

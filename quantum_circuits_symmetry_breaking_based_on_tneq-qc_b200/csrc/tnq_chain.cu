@@ -1,0 +1,368 @@
+// tnq_chain.cu -- register-resident sweep for single-layer MPS networks (the reference's default
+// graph: QCTNHelper.generate_example_graph(graph_type="mps"), examples/example_train_single_node.py,
+// tests/test_probabilities.py), real float32, edge rank K in {2, 3, 4}.
+//
+// For this family every greedy group (tneq_qc/contractor/greedy_strategy.py:690-990) has the form
+//     "cdef,aeg,higj,ahc,d,i->ajf":  env'[j,f] = sum Ls[c,e,f] M[e,g] Ls[h,g,j] env[h,c]
+// with Ls[c,e,f] = sum_d G[c,d,e,f] s[d] (core folded with the next qubit's circuit state), the first
+// group being the same formula with env = s0 s0^T, and the last one "acd,adc->a" a trace against M.
+// The environment is K x K: it lives in REGISTERS.  One thread owns one sample and walks all n qubits:
+//   T1[h,e,f] = env[h,c] Ls[c,e,f] ; T2[h,g,f] = T1[h,e,f] M[e,g] ; env'[j,f] = T2[h,g,f] Ls[h,g,j]
+// (3 K^4 FMAs per qubit, everything unrolled at compile time, Ls read as shared-memory broadcasts,
+// M streamed from HBM once: 4 K^2 bytes per qubit and sample -- the kernel's only real traffic).
+// Training fuses the loss (engine_siamese.py:490-530) and the reverse sweep: the n left environments
+// are kept per thread (local memory, L1 resident), the sweep runs back down the chain, and the
+// per-sample core-gradient contributions are combined with warp shuffles, then per CTA, then by a
+// small finalize kernel in a fixed order (deterministic).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "tneq_b200.h"
+
+extern int tnq_internal_fail(const std::string& msg);
+extern int tnq_internal_cuda_fail(cudaError_t e, const char* what);
+extern void tnq_internal_count_launch();
+
+namespace {
+
+constexpr int MAXQ = TNQ_CHAIN_MAX_QUBITS;
+constexpr int CHAIN_THREADS = 128;
+
+struct ChainArgs {
+    const float* core[MAXQ];     // n-1 cores, each [K][K][K][K] = G[c,d,e,f]
+    const float* state[MAXQ];    // n circuit states, each [K]
+    const float* mx[MAXQ];       // n measurement tensors, sample b at mx[q] + b * mx_stride[q], [K][K] row major
+    long long mx_stride[MAXQ];
+    float* grad[MAXQ];           // n-1 gradient outputs [K][K][K][K] (train / bwd)
+    int n;
+};
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one step of the chain, forward: env <- step(env, Ls, M)
+template <int K>
+__device__ __forceinline__ void chain_step(float (&env)[K][K], const float* __restrict__ Ls, const float (&M)[K][K]) {
+    float T1[K][K][K];   // [h][e][f]
+#pragma unroll
+    for (int h = 0; h < K; ++h)
+#pragma unroll
+        for (int e = 0; e < K; ++e)
+#pragma unroll
+            for (int f = 0; f < K; ++f) {
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < K; ++c) s = fmaf(env[h][c], Ls[(c * K + e) * K + f], s);
+                T1[h][e][f] = s;
+            }
+    float T2[K][K][K];   // [h][g][f]
+#pragma unroll
+    for (int h = 0; h < K; ++h)
+#pragma unroll
+        for (int g = 0; g < K; ++g)
+#pragma unroll
+            for (int f = 0; f < K; ++f) {
+                float s = 0.f;
+#pragma unroll
+                for (int e = 0; e < K; ++e) s = fmaf(T1[h][e][f], M[e][g], s);
+                T2[h][g][f] = s;
+            }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int f = 0; f < K; ++f) {
+            float s = 0.f;
+#pragma unroll
+            for (int h = 0; h < K; ++h)
+#pragma unroll
+                for (int g = 0; g < K; ++g) s = fmaf(T2[h][g][f], Ls[(h * K + g) * K + j], s);
+            env[j][f] = s;
+        }
+}
+
+template <int K>
+__device__ __forceinline__ void load_m(float (&M)[K][K], const float* __restrict__ p, bool valid) {
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) M[i][j] = valid ? __ldg(p + i * K + j) : 0.f;
+}
+
+// MODE 0: values only.  MODE 1: fused loss + gradients.  MODE 2: gradients seeded by `seed` (autograd).
+template <int K, int MODE>
+__global__ void __launch_bounds__(CHAIN_THREADS)
+tnq_chain_kernel(const __grid_constant__ ChainArgs a, long long B, const float* __restrict__ seed,
+                 float* __restrict__ values, float* __restrict__ partials, float log_scale, float inv_count) {
+    constexpr int K3 = K * K * K;
+    extern __shared__ float sm[];
+    const int n = a.n;
+    float* Ls = sm;                                   // [n-1][K3]
+    float* wacc = sm + (n - 1) * K3;                  // [warps][(n-1) * K3 + 1] gradient / loss accumulators
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int acc_stride = (n - 1) * K3 + 1;
+    // Ls[q][c][e][f] = sum_d G_q[c,d,e,f] s_{q+1}[d]
+    for (int i = threadIdx.x; i < (n - 1) * K3; i += blockDim.x) {
+        const int q = i / K3, r = i % K3, c = r / (K * K), e = (r / K) % K, f = r % K;
+        float s = 0.f;
+        for (int d = 0; d < K; ++d) s = fmaf(__ldg(a.core[q] + ((c * K + d) * K + e) * K + f), __ldg(a.state[q + 1] + d), s);
+        Ls[i] = s;
+    }
+    if (MODE != 0)
+        for (int i = threadIdx.x; i < warps * acc_stride; i += blockDim.x) wacc[i] = 0.f;
+    __syncthreads();
+    float s0[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) s0[i] = __ldg(a.state[0] + i);
+    float* my_acc = wacc + warp * acc_stride;
+
+    const long long nwarp_iters = (B + 31) / 32;
+    for (long long wi = (long long)blockIdx.x * warps + warp; wi < nwarp_iters; wi += (long long)gridDim.x * warps) {
+        const long long b = wi * 32 + lane;
+        const bool valid = b < B;
+        float env[K][K];
+#pragma unroll
+        for (int h = 0; h < K; ++h)
+#pragma unroll
+            for (int c = 0; c < K; ++c) env[h][c] = s0[h] * s0[c];
+        float tape[MODE != 0 ? MAXQ : 1][K][K];       // left environments (local memory when training)
+        float M[K][K];
+        for (int q = 0; q < n - 1; ++q) {
+            if (MODE != 0) {
+#pragma unroll
+                for (int h = 0; h < K; ++h)
+#pragma unroll
+                    for (int c = 0; c < K; ++c) tape[q][h][c] = env[h][c];
+            }
+            load_m<K>(M, a.mx[q] + b * a.mx_stride[q], valid);
+            chain_step<K>(env, Ls + q * K3, M);
+        }
+        load_m<K>(M, a.mx[n - 1] + b * a.mx_stride[n - 1], valid);
+        float val = 0.f;                               // "acd,adc->a"
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int d = 0; d < K; ++d) val = fmaf(env[c][d], M[d][c], val);
+        if (MODE != 2 && values != nullptr && valid) values[b] = val;
+        if (MODE == 0) continue;
+
+        // ---- seed: d loss / d value ----
+        float dval;
+        if (MODE == 1) {
+            const float clamped = fmaxf(val, 1e-10f);
+            float lpart = valid ? -(logf(clamped) + log_scale) * inv_count : 0.f;
+            lpart = warp_sum(lpart);
+            if (lane == 0) my_acc[acc_stride - 1] += lpart;
+            dval = (valid && val >= 1e-10f) ? -inv_count / clamped : 0.f;
+        } else {
+            dval = valid ? __ldg(seed + b) : 0.f;
+        }
+        float denv[K][K];                              // adjoint of the environment after the last step
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int d = 0; d < K; ++d) denv[c][d] = dval * M[d][c];
+
+        // ---- reverse sweep ----
+        for (int q = n - 2; q >= 0; --q) {
+            const float* L = Ls + q * K3;
+            load_m<K>(M, a.mx[q] + b * a.mx_stride[q], valid);
+            float e0[K][K];
+#pragma unroll
+            for (int h = 0; h < K; ++h)
+#pragma unroll
+                for (int c = 0; c < K; ++c) e0[h][c] = tape[q][h][c];
+            // recompute T1[h][e][f], T2[h][g][f]
+            float T1[K][K][K], T2[K][K][K];
+#pragma unroll
+            for (int h = 0; h < K; ++h)
+#pragma unroll
+                for (int e = 0; e < K; ++e)
+#pragma unroll
+                    for (int f = 0; f < K; ++f) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int c = 0; c < K; ++c) s = fmaf(e0[h][c], L[(c * K + e) * K + f], s);
+                        T1[h][e][f] = s;
+                    }
+#pragma unroll
+            for (int h = 0; h < K; ++h)
+#pragma unroll
+                for (int g = 0; g < K; ++g)
+#pragma unroll
+                    for (int f = 0; f < K; ++f) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int e = 0; e < K; ++e) s = fmaf(T1[h][e][f], M[e][g], s);
+                        T2[h][g][f] = s;
+                    }
+            float* gq = my_acc + q * K3;
+            // R role: dLs[h][g][j] += sum_f T2[h][g][f] denv[j][f] ; dT2[h][g][f] = sum_j denv[j][f] Ls[h][g][j]
+#pragma unroll
+            for (int h = 0; h < K; ++h)
+#pragma unroll
+                for (int g = 0; g < K; ++g) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int f = 0; f < K; ++f) s = fmaf(T2[h][g][f], denv[j][f], s);
+                        s = warp_sum(s);
+                        if (lane == 0) gq[(h * K + g) * K + j] += s;
+                    }
+#pragma unroll
+                    for (int f = 0; f < K; ++f) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int j = 0; j < K; ++j) s = fmaf(denv[j][f], L[(h * K + g) * K + j], s);
+                        T2[h][g][f] = s;                       // T2 now holds dT2
+                    }
+                }
+            // dT1[h][e][f] = sum_g dT2[h][g][f] M[e][g]   (T1 still needed for nothing else -> keep e0 for dLs_L)
+            float dT1[K][K][K];
+#pragma unroll
+            for (int h = 0; h < K; ++h)
+#pragma unroll
+                for (int e = 0; e < K; ++e)
+#pragma unroll
+                    for (int f = 0; f < K; ++f) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int g = 0; g < K; ++g) s = fmaf(T2[h][g][f], M[e][g], s);
+                        dT1[h][e][f] = s;
+                    }
+            // L role: dLs[c][e][f] += sum_h e0[h][c] dT1[h][e][f] ; denv[h][c] = sum_{e,f} dT1[h][e][f] Ls[c][e][f]
+#pragma unroll
+            for (int c = 0; c < K; ++c)
+#pragma unroll
+                for (int e = 0; e < K; ++e)
+#pragma unroll
+                    for (int f = 0; f < K; ++f) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int h = 0; h < K; ++h) s = fmaf(e0[h][c], dT1[h][e][f], s);
+                        s = warp_sum(s);
+                        if (lane == 0) gq[(c * K + e) * K + f] += s;
+                    }
+#pragma unroll
+            for (int h = 0; h < K; ++h)
+#pragma unroll
+                for (int c = 0; c < K; ++c) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int e = 0; e < K; ++e)
+#pragma unroll
+                        for (int f = 0; f < K; ++f) s = fmaf(dT1[h][e][f], L[(c * K + e) * K + f], s);
+                    denv[h][c] = s;
+                }
+        }
+    }
+    if (MODE != 0) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < acc_stride; i += blockDim.x) {
+            float s = 0.f;
+            for (int w = 0; w < warps; ++w) s += wacc[w * acc_stride + i];
+            partials[(size_t)blockIdx.x * acc_stride + i] = s;
+        }
+    }
+}
+
+// dG_q[c,d,e,f] = dLs_q[c,e,f] * s_{q+1}[d] ; loss
+template <int K>
+__global__ void tnq_chain_finalize_kernel(const __grid_constant__ ChainArgs a, const float* __restrict__ partials, int nparts,
+                                          float* __restrict__ loss) {
+    constexpr int K3 = K * K * K;
+    const int acc_stride = (a.n - 1) * K3 + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= acc_stride) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * acc_stride + i];
+    if (i == acc_stride - 1) {
+        if (loss) *loss = s;
+        return;
+    }
+    const int q = i / K3, r = i % K3, c = r / (K * K), e = (r / K) % K, f = r % K;
+    for (int d = 0; d < K; ++d) a.grad[q][((c * K + d) * K + e) * K + f] = s * __ldg(a.state[q + 1] + d);
+}
+
+template <int K>
+int launch_chain(const ChainArgs& a, long long B, int mode, const float* seed, float* values, float* loss,
+                 float log_scale, void* workspace, long long ws_bytes, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int K3 = K * K * K, warps = CHAIN_THREADS / 32;
+    const int acc_stride = (a.n - 1) * K3 + 1;
+    const size_t smem = sizeof(float) * ((size_t)(a.n - 1) * K3 + (mode ? (size_t)warps * acc_stride : 0));
+    long long want = (B + CHAIN_THREADS - 1) / CHAIN_THREADS;
+    const long long cap = (long long)sms * (mode ? 4 : 8);
+    const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    float* partials = reinterpret_cast<float*>(workspace);
+    if (mode != 0 && (size_t)ws_bytes < sizeof(float) * (size_t)grid * acc_stride)
+        return tnq_internal_fail("tnq_mps_chain: workspace too small");
+    const float inv = 1.0f / (float)B;
+    cudaError_t e = cudaSuccess;
+    if (mode == 0) {
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(tnq_chain_kernel<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tnq_chain_kernel<K, 0><<<grid, CHAIN_THREADS, smem, st>>>(a, B, seed, values, partials, log_scale, inv);
+    } else if (mode == 1) {
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(tnq_chain_kernel<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tnq_chain_kernel<K, 1><<<grid, CHAIN_THREADS, smem, st>>>(a, B, seed, values, partials, log_scale, inv);
+    } else {
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(tnq_chain_kernel<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tnq_chain_kernel<K, 2><<<grid, CHAIN_THREADS, smem, st>>>(a, B, seed, values, partials, log_scale, inv);
+    }
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(chain)");
+    tnq_internal_count_launch();
+    if (mode != 0) {
+        tnq_chain_finalize_kernel<K><<<(acc_stride + 127) / 128, 128, 0, st>>>(a, partials, grid, mode == 1 ? loss : nullptr);
+        tnq_internal_count_launch();
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_mps_chain launch");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t tnq_mps_chain_workspace_bytes(int K, int n, int64_t B) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int64_t)sizeof(float) * (int64_t)sms * 8 * ((int64_t)(n - 1) * K * K * K + 1) + 256;
+}
+
+int tnq_mps_chain(int K, int n, const float* const* cores, const float* const* states, const float* const* mx,
+                  const int64_t* mx_stride, int64_t B, int mode, const float* seed, float* values, float* loss,
+                  float* const* grads, double log_scale, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (n < 2 || n > MAXQ) return tnq_internal_fail("tnq_mps_chain: between 2 and " + std::to_string(MAXQ) + " qubits");
+    if (K < 2 || K > 4) return tnq_internal_fail("tnq_mps_chain: edge rank must be 2, 3 or 4");
+    if (!cores || !states || !mx || !mx_stride || B <= 0 || mode < 0 || mode > 2) return tnq_internal_fail("tnq_mps_chain: bad arguments");
+    if (mode != 0 && (!grads || !workspace)) return tnq_internal_fail("tnq_mps_chain: gradients need grads[] and a workspace");
+    if (mode == 2 && !seed) return tnq_internal_fail("tnq_mps_chain: mode 2 needs a seed");
+    ChainArgs a;
+    a.n = n;
+    for (int q = 0; q < n; ++q) {
+        a.state[q] = states[q];
+        a.mx[q] = mx[q];
+        a.mx_stride[q] = mx_stride[q];
+        a.core[q] = q < n - 1 ? cores[q] : nullptr;
+        a.grad[q] = (mode != 0 && q < n - 1) ? grads[q] : nullptr;
+        if (!states[q] || !mx[q] || (q < n - 1 && (!cores[q] || (mode != 0 && !grads[q]))))
+            return tnq_internal_fail("tnq_mps_chain: null pointer at qubit " + std::to_string(q));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (K) {
+        case 2: return launch_chain<2>(a, B, mode, seed, values, loss, (float)log_scale, workspace, workspace_bytes, st);
+        case 3: return launch_chain<3>(a, B, mode, seed, values, loss, (float)log_scale, workspace, workspace_bytes, st);
+        default: return launch_chain<4>(a, B, mode, seed, values, loss, (float)log_scale, workspace, workspace_bytes, st);
+    }
+}
+
+}  // extern "C"

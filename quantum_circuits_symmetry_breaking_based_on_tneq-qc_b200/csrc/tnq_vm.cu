@@ -733,7 +733,8 @@ int plan_geometry(const tnq_plan* pl, long long nsamples, Geometry* g) {
     if (per_sm > 4) per_sm = 4;
     g->threads = per_sm == 1 ? 512 : 256;   // registers allow 512 x 128 or 2 x 256 x 128 per SM
     if (per_sm > 2) per_sm = 2;
-    if (const char* e = getenv("TNQ_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
+    if (const char* e = getenv("TNQ_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) per_sm = v; }
+    if (const char* e = getenv("TNQ_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) g->threads = v; }
     long long grid = (long long)pl->sm_count * per_sm;
     if (grid > g->ntiles) grid = g->ntiles;
     g->grid = (int)grid;

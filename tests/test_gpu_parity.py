@@ -51,11 +51,24 @@ CASES = [
     ("merged", 4, 2, 9, "complex64", "a"),
     ("mps", 6, 3, 10, "float32", "ab"),
     ("mps", 4, 4, 130, "float32", "a"),
+    ("mps", 2, 2, 70, "float32", "a"),
+    ("mps", 24, 2, 1000, "float32", "a"),
 ]
 
 
+@pytest.fixture(params=["default-route", "vm-only"])
+def route(request):
+    """single-layer MPS float32 networks take the register-resident chain kernel by default;
+    'vm-only' forces the same cases through the generic contraction VM as well."""
+    import os
+    if request.param == "vm-only":
+        os.environ["TNQ_NO_CHAIN"] = "1"
+    yield request.param
+    os.environ.pop("TNQ_NO_CHAIN", None)
+
+
 @pytest.mark.parametrize("kind,n,K,B,dtype,mode", CASES)
-def test_forward_and_training_step(kind, n, K, B, dtype, mode, built_lib):
+def test_forward_and_training_step(kind, n, K, B, dtype, mode, built_lib, route):
     """Probabilities, loss and core gradients of the CUDA path vs the oracle on the same inputs.
     Tolerance 1e-5 relative (north_star) for float32/complex64, measured per tensor against its
     largest entry, on well-conditioned samples (see helpers.well_conditioned_case); 1e-11 for
@@ -77,6 +90,9 @@ def test_forward_and_training_step(kind, n, K, B, dtype, mode, built_lib):
         q.cores_weights[k] = v.to(dev).requires_grad_(True)
     st = [s.to(dev) for s in states]
     got = eng.contract_with_compiled_strategy(q, st, [_to_dev(m, dev) for m in clone_mx(mxs)])
+    bound = next(iter(eng._compiled(q, st, [_to_dev(m, dev) for m in clone_mx(mxs)], True, "symmetric").plans.values()))
+    expect_chain = route == "default-route" and kind == "mps" and dtype == "float32" and mode == "a" and K <= 4
+    assert bool(bound.chain_rank) == expect_chain
     assert got.shape == want.shape and got.dtype == want.dtype
     assert rel_err(got, want) < tol
     assert elem_rel_err(got.double(), truth) < max(tol, 3 * elem_rel_err(want.double(), truth))
