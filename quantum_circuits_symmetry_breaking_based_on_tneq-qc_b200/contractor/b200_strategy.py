@@ -161,15 +161,17 @@ class _Call:
         K, n, dev = self.bound.chain_rank, self.bound.plan.nqubits, self.bound.device
         by_key = dict(zip(self.core_keys, cores))
         order = [k for k in self.bound.plan.core_shapes]                   # ('core', name) in qctn.cores order
-        cs = [by_key[k].detach().contiguous() for k in order]
-        sts = [self.states[q].detach().contiguous() for q in range(n)]
+        cs = [c if c.is_contiguous() else c.contiguous() for c in (by_key[k] for k in order)]
+        sts = [t if t.is_contiguous() else t.contiguous() for t in (self.states[q] for q in range(n))]
         ms, strides = [], []
         for q in range(n):
-            m = self.mxs[q].detach()
-            if m.stride(-1) != 1 or m.stride(-2) != K:
+            m = self.mxs[q]
+            st = m.stride()
+            if st[-1] != 1 or st[-2] != K:
                 m = m.contiguous()
+                st = m.stride()
             ms.append(m)
-            strides.append(0 if (m.shape[0] == 1 and self.B != 1) else m.stride(0))
+            strides.append(0 if (m.shape[0] == 1 and self.B != 1) else st[0])
         ws_bytes = int(lib.tnq_mps_chain_workspace_bytes(K, n, self.B))
         if self.bound._chain_ws is None or self.bound._chain_ws.numel() < ws_bytes:
             self.bound._chain_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)

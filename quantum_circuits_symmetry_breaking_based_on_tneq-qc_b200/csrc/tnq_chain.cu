@@ -94,6 +94,38 @@ __device__ __forceinline__ void load_m(float (&M)[K][K], const float* __restrict
         for (int j = 0; j < K; ++j) M[i][j] = valid ? __ldg(p + i * K + j) : 0.f;
 }
 
+// Coalesced fetch of one qubit's measurement matrices for the 32 samples of a warp: when the batch
+// is contiguous (stride K*K) the 32*K*K floats are one contiguous run, read with K*K fully
+// coalesced loads into registers (raw[i] = run[lane + 32 i]) ...
+template <int K>
+__device__ __forceinline__ void fetch_m(float (&raw)[K * K], const float* __restrict__ base, long long b0, long long B,
+                                        int lane) {
+    const long long total = (B - b0 < 32 ? B - b0 : 32) * (K * K);
+    const float* p = base + b0 * (K * K);
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) {
+        const int idx = lane + 32 * i;
+        raw[i] = idx < total ? __ldg(p + idx) : 0.f;
+    }
+}
+// ... and transposed through a per-warp shared-memory slab into per-lane matrices (stride K*K is odd
+// for K = 3 and the slab is padded for K = 2, 4, so both sides are conflict free).
+template <int K>
+__device__ __forceinline__ void unpack_m(float (&M)[K][K], const float (&raw)[K * K], float* slab, int lane) {
+    constexpr int LD = (K * K) | 1;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) {
+        const int idx = lane + 32 * i;
+        slab[(idx / (K * K)) * LD + idx % (K * K)] = raw[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) M[i][j] = slab[lane * LD + i * K + j];
+}
+
 // MODE 0: values only.  MODE 1: fused loss + gradients.  MODE 2: gradients seeded by `seed` (autograd).
 template <int K, int MODE>
 __global__ void __launch_bounds__(CHAIN_THREADS)
@@ -103,9 +135,13 @@ tnq_chain_kernel(const __grid_constant__ ChainArgs a, long long B, const float* 
     extern __shared__ float sm[];
     const int n = a.n;
     float* Ls = sm;                                   // [n-1][K3]
-    float* wacc = sm + (n - 1) * K3;                  // [warps][(n-1) * K3 + 1] gradient / loss accumulators
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int SLAB = 32 * ((K * K) | 1);
+    float* slab = sm + (n - 1) * K3 + warp * SLAB;    // per-warp staging of one qubit's Mx
+    float* wacc = sm + (n - 1) * K3 + warps * SLAB;   // [warps][(n-1) * K3 + 1] gradient / loss accumulators
     const int acc_stride = (n - 1) * K3 + 1;
+    bool packed = true;                               // every Mx contiguous over the batch?
+    for (int q = 0; q < n; ++q) packed = packed && (a.mx_stride[q] == K * K);
     // Ls[q][c][e][f] = sum_d G_q[c,d,e,f] s_{q+1}[d]
     for (int i = threadIdx.x; i < (n - 1) * K3; i += blockDim.x) {
         const int q = i / K3, r = i % K3, c = r / (K * K), e = (r / K) % K, f = r % K;
@@ -131,7 +167,14 @@ tnq_chain_kernel(const __grid_constant__ ChainArgs a, long long B, const float* 
 #pragma unroll
             for (int c = 0; c < K; ++c) env[h][c] = s0[h] * s0[c];
         float tape[MODE != 0 ? MAXQ : 1][K][K];       // left environments (local memory when training)
-        float M[K][K];
+        float M[K][K], Mn[K][K], raw[K * K];
+        const long long b0 = wi * 32;
+        if (packed) {
+            fetch_m<K>(raw, a.mx[0], b0, B, lane);
+            unpack_m<K>(M, raw, slab, lane);
+        } else {
+            load_m<K>(M, a.mx[0] + b * a.mx_stride[0], valid);
+        }
         for (int q = 0; q < n - 1; ++q) {
             if (MODE != 0) {
 #pragma unroll
@@ -139,10 +182,21 @@ tnq_chain_kernel(const __grid_constant__ ChainArgs a, long long B, const float* 
 #pragma unroll
                     for (int c = 0; c < K; ++c) tape[q][h][c] = env[h][c];
             }
-            load_m<K>(M, a.mx[q] + b * a.mx_stride[q], valid);
+            // next qubit's Mx is in flight while this one is consumed
+            if (packed)
+                fetch_m<K>(raw, a.mx[q + 1], b0, B, lane);
+            else
+                load_m<K>(Mn, a.mx[q + 1] + b * a.mx_stride[q + 1], valid);
             chain_step<K>(env, Ls + q * K3, M);
+            if (packed) {
+                unpack_m<K>(M, raw, slab, lane);
+            } else {
+#pragma unroll
+                for (int i = 0; i < K; ++i)
+#pragma unroll
+                    for (int j = 0; j < K; ++j) M[i][j] = Mn[i][j];
+            }
         }
-        load_m<K>(M, a.mx[n - 1] + b * a.mx_stride[n - 1], valid);
         float val = 0.f;                               // "acd,adc->a"
 #pragma unroll
         for (int c = 0; c < K; ++c)
@@ -169,9 +223,22 @@ tnq_chain_kernel(const __grid_constant__ ChainArgs a, long long B, const float* 
             for (int d = 0; d < K; ++d) denv[c][d] = dval * M[d][c];
 
         // ---- reverse sweep ----
+        if (packed)
+            fetch_m<K>(raw, a.mx[n - 2], b0, B, lane);
+        else
+            load_m<K>(Mn, a.mx[n - 2] + b * a.mx_stride[n - 2], valid);
         for (int q = n - 2; q >= 0; --q) {
             const float* L = Ls + q * K3;
-            load_m<K>(M, a.mx[q] + b * a.mx_stride[q], valid);
+            if (packed) {
+                unpack_m<K>(M, raw, slab, lane);
+                if (q > 0) fetch_m<K>(raw, a.mx[q - 1], b0, B, lane);
+            } else {
+#pragma unroll
+                for (int i = 0; i < K; ++i)
+#pragma unroll
+                    for (int j = 0; j < K; ++j) M[i][j] = Mn[i][j];
+                if (q > 0) load_m<K>(Mn, a.mx[q - 1] + b * a.mx_stride[q - 1], valid);
+            }
             float e0[K][K];
 #pragma unroll
             for (int h = 0; h < K; ++h)
@@ -298,7 +365,8 @@ int launch_chain(const ChainArgs& a, long long B, int mode, const float* seed, f
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int K3 = K * K * K, warps = CHAIN_THREADS / 32;
     const int acc_stride = (a.n - 1) * K3 + 1;
-    const size_t smem = sizeof(float) * ((size_t)(a.n - 1) * K3 + (mode ? (size_t)warps * acc_stride : 0));
+    const size_t smem = sizeof(float) * ((size_t)(a.n - 1) * K3 + (size_t)warps * 32 * ((K * K) | 1) +
+                                         (mode ? (size_t)warps * acc_stride : 0));
     long long want = (B + CHAIN_THREADS - 1) / CHAIN_THREADS;
     const long long cap = (long long)sms * (mode ? 4 : 8);
     const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
