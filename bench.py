@@ -263,7 +263,7 @@ def main():
     engine = tb.EngineSiamese(backend=backend, strategy_mode="balanced", mx_K=K)
     qctn = tb.QCTN(graph, backend=backend)
     for c in names:
-        w = cores_cpu[c].to(dev).clone()
+        w = cores_cpu[c].to(dev).clone(memory_format=torch.contiguous_format)
         if dist is not None:                   # the reference forgets this
             dist.broadcast(torch.view_as_real(w) if w.is_complex() else w, src=0)
         qctn.cores_weights[c] = w.requires_grad_(True)

@@ -131,6 +131,19 @@ int tnq_cplx_expand_f32(const float* in, float* out, int ndim, const int64_t* ou
 int tnq_cplx_fold_f32(const float* in, float* out, int ndim, const int64_t* out_dims, const int64_t* in_strides,
                       int64_t ri_stride, int64_t ro_stride, int conj, int accumulate, void* stream);
 
+/*
+ * The optimizer step of the reference's default method ('sgdg': SGD on the Stiefel manifold by a
+ * Cayley transform, backend_pytorch.py:349-468) for all cores of a network in one launch.
+ * Core i is a row-major rows[i] x cols[i] float32 matrix (rows = product of the first half of its
+ * dims, backend_pytorch.py:364-368) with rows[i] <= cols[i] <= TNQ_SGDG_MAX_COLS; velocity[i] is the
+ * cols[i] x rows[i] momentum buffer.  params and velocity are updated in place; the pointer tables
+ * and rows/cols are DEVICE arrays of ncores entries.  The reference's 1 % random QR retraction
+ * (backend_pytorch.py:382) is the caller's business.
+ */
+#define TNQ_SGDG_MAX_COLS 64
+int tnq_sgdg_step(float* const* params, const float* const* grads, float* const* velocity, const int* rows,
+                  const int* cols, int ncores, int max_cols, float lr, float momentum, void* stream);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t tnq_launch_count(void);
 

@@ -112,7 +112,14 @@ class NcclComm:
 
     def broadcast_tensor(self, tensor: torch.Tensor, src: int = 0) -> torch.Tensor:
         if self._initialized and self.world_size > 1:
-            dist.broadcast(torch.view_as_real(tensor) if tensor.is_complex() else tensor, src=src)
+            real = torch.view_as_real(tensor) if tensor.is_complex() else tensor
+            if real.is_contiguous():
+                dist.broadcast(real, src=src)
+            else:                                   # e.g. a core made by init_random_core (a transposed view)
+                buf = real.detach().contiguous()
+                dist.broadcast(buf, src=src)
+                with torch.no_grad():
+                    real.copy_(buf)
         return tensor
 
     def broadcast_tensors_packed(self, tensors: Sequence[torch.Tensor], src: int = 0):

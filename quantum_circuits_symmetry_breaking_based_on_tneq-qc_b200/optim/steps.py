@@ -6,9 +6,10 @@ Stiefel-manifold SGD with a Cayley retraction used by the examples
 (examples/example_train_single_node.py:229-240).  Params may be TNTensors:
 the update acts on tensor*scale with grad/scale and re-wraps (:205-266).
 
-These are small dense per-core operations (K^2 x K^2 matrices); they run on the
-device through torch for now -- SURVEY 8(f) item 1 lists a batched CUDA kernel
-for them as the next step after the contraction path.
+These are small dense per-core operations (K^2 x K^2 matrices).  'sgdg', the
+method the examples use, runs for all float32 cores of a network as ONE launch
+of csrc/tnq_sgdg.cu (one CTA per core); the other methods, complex cores and
+cores wider than TNQ_SGDG_MAX_COLS go through torch on the device.
 """
 from __future__ import annotations
 
@@ -104,14 +105,85 @@ def _rmsprop(params, grads, state, hp):
     return out, state
 
 
+SGDG_MAX_COLS = 64          # TNQ_SGDG_MAX_COLS, include/tneq_b200.h
+
+
+def _matrix_shape(shp):
+    if len(shp) > 2:
+        rows = int(np.prod(shp[: len(shp) // 2]))
+        return rows, int(np.prod(shp)) // max(rows, 1)
+    return (int(shp[0]), int(shp[1])) if len(shp) == 2 else (0, 0)
+
+
+def _qr_retract(unity):
+    qm, rm = torch.linalg.qr(unity.T, mode="reduced")
+    d = torch.diag(rm)
+    return (qm * (torch.sgn(d) if torch.is_complex(d) else torch.sign(d)).unsqueeze(0)).T
+
+
+def _sgdg_kernel_step(idx, params, grads, state, lr, mom, out):
+    """All eligible cores in one launch of tnq_sgdg_step (csrc/tnq_sgdg.cu)."""
+    from .. import _lib
+    lib = _lib.load()
+    dev = params[idx[0]].device
+    shapes = [_matrix_shape(params[i].shape) for i in idx]
+    sizes = [r * c for r, c in shapes]
+    with torch.cuda.device(dev):
+        # the update is in place on the device, the reference returns fresh tensors: work on a packed copy
+        flat = torch.cat([params[i].reshape(-1) for i in idx])
+        gs = [grads[i].contiguous() for i in idx]
+        for n, i in enumerate(idx):
+            # the reference draws one random number per Stiefel core (backend_pytorch.py:382)
+            if random.randint(1, 101) == 1:
+                r, c = shapes[n]
+                off = sum(sizes[:n])
+                x = flat[off: off + sizes[n]].view(r, c)
+                x.copy_(_qr_retract(x / (torch.norm(x, p=2, dim=1, keepdim=True) + 1e-8)))
+            if state["momentum_buffer"][i] is None:
+                r, c = shapes[n]
+                state["momentum_buffer"][i] = torch.zeros(c, r, dtype=torch.float32, device=dev)
+            elif not state["momentum_buffer"][i].is_contiguous():
+                state["momentum_buffer"][i] = state["momentum_buffer"][i].contiguous()
+        vs = [state["momentum_buffer"][i] for i in idx]
+        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]) * 4
+        table = np.empty((3, len(idx)), dtype=np.int64)
+        table[0] = flat.data_ptr() + offs
+        table[1] = [g.data_ptr() for g in gs]
+        table[2] = [v.data_ptr() for v in vs]
+        key = tuple(shapes)
+        if state.get("_sgdg_dims_key") != key:
+            state["_sgdg_dims_key"] = key
+            state["_sgdg_dims"] = torch.tensor([[r for r, _ in shapes], [c for _, c in shapes]], dtype=torch.int32,
+                                               device=dev)
+        dims = state["_sgdg_dims"]
+        tdev = torch.from_numpy(table).to(dev)
+        _lib.check(lib.tnq_sgdg_step(tdev[0].data_ptr(), tdev[1].data_ptr(), tdev[2].data_ptr(), dims[0].data_ptr(),
+                                     dims[1].data_ptr(), len(idx), max(c for _, c in shapes), float(lr), float(mom),
+                                     torch.cuda.current_stream().cuda_stream))
+    off = 0
+    for n, i in enumerate(idx):
+        out[i] = flat[off: off + sizes[n]].view(params[i].shape)
+        off += sizes[n]
+
+
 def _sgdg(params, grads, state, hp):
     """Cayley-transform SGD on the Stiefel manifold (backend_pytorch.py:349-468)."""
     lr, mom, stiefel = hp.get("learning_rate", 0.01), hp.get("momentum", 0.0), hp.get("stiefel", True)
     eps = 1e-8
     if "momentum_buffer" not in state:
         state["momentum_buffer"] = [None] * len(params)
-    out = []
+    out = [None] * len(params)
+    fast = []
+    if stiefel and hp.get("device_kernel", True):
+        for i, (p, g) in enumerate(zip(params, grads)):
+            r, c = _matrix_shape(p.shape)
+            if (p.is_cuda and p.dtype == torch.float32 and g.dtype == torch.float32 and 1 <= r <= c <= SGDG_MAX_COLS):
+                fast.append(i)
+    if fast:
+        _sgdg_kernel_step(fast, params, grads, state, lr, mom, out)
     for i, (p, g) in enumerate(zip(params, grads)):
+        if out[i] is not None:
+            continue
         shp = p.shape
         if len(shp) > 2:
             rows = int(np.prod(shp[: len(shp) // 2]))
@@ -121,12 +193,10 @@ def _sgdg(params, grads, state, hp):
         cplx = torch.is_complex(x)
         unity = x / (torch.norm(x, p=2, dim=1, keepdim=True) + eps)
         if not (stiefel and unity.shape[0] <= unity.shape[1]):
-            out.append(p - lr * g)
+            out[i] = p - lr * g
             continue
         if random.randint(1, 101) == 1:  # occasional QR retraction, same RNG stream as the reference
-            qm, rm = torch.linalg.qr(unity.T, mode="reduced")
-            d = torch.diag(rm)
-            unity = (qm * (torch.sgn(d) if torch.is_complex(d) else torch.sign(d)).unsqueeze(0)).T
+            unity = _qr_retract(unity)
         if state["momentum_buffer"][i] is None:
             state["momentum_buffer"][i] = torch.zeros(gx.T.shape, dtype=gx.dtype, device=p.device)
         hconj = (lambda m: torch.conj(m).T) if cplx else (lambda m: m.T)
@@ -139,6 +209,6 @@ def _sgdg(params, grads, state, hp):
         eye = torch.eye(w.shape[0], dtype=w.dtype, device=w.device)
         y = torch.inverse(eye - (alpha / 2) * w) @ (eye + (alpha / 2) * w) @ hconj(unity)
         pn = hconj(y)
-        out.append(pn.reshape(shp) if len(shp) > 2 else pn)
+        out[i] = pn.reshape(shp) if len(shp) > 2 else pn
         state["momentum_buffer"][i] = w @ hconj(unity)
     return out, state
