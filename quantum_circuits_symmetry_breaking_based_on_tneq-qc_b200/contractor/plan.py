@@ -92,6 +92,42 @@ class ContractionPlan:
         K = ranks.pop()
         return K if 2 <= K <= 4 else 0
 
+    def mps_ladder(self):
+        """(K, [A_0..A_{n-2}], [X_0..X_{n-2}]) if this is the two-layer merged MPS sweep
+        (QCTN.merge(mps_n, mps_n), reference qctn.py:1296-1506) that the warp-level ladder kernel
+        covers (csrc/tnq_ladder.cu): float32, uniform edge rank 2 or 3, circuit states and plain
+        (B,K,K) measurements on every qubit, n >= 3; else None.  A_q / X_q are the core names of the
+        first / second layer acting on wires (q, q+1), read off the operands of the greedy groups
+        (the bit-exact bookkeeping stays the plan compiler's; the kernel only re-associates the
+        arithmetic inside a group)."""
+        n = self.nqubits
+        eq = self.schedule.equations
+        if self.dtype != "float32" or self.nb != 1 or n < 3 or n > 64 or len(eq) != n:
+            return None
+        want = (["cdef,eghi,c,ahj,klmn,mojp,k,d,l->agnpfio"]
+                + ["cdef,ghij,aik,lmno,pqkr,aelpcgn,d,m->ahorfjq"] * (n - 3)
+                + ["cdef,gfhi,ahj,klmn,onjp,aekocgm,d,l->api", "acd,adc->a"])
+        if eq != want or len(self.core_shapes) != 2 * (n - 1) or any(k[0] != "core" for k in self.core_shapes):
+            return None
+        ranks = {d for shp in self.core_shapes.values() for d in shp}
+        for st in self.schedule.steps:
+            ranks |= set(st.dims.values())
+        if len(ranks) != 1:
+            return None
+        K = ranks.pop()
+        if K not in (2, 3):
+            return None
+        layer1, layer2 = [], []
+        for q in range(n - 1):
+            ops = self.schedule.steps[q].operands
+            if ops[0].kind != "core" or ops[1].kind != "core":
+                return None
+            layer1.append(ops[0].key)
+            layer2.append(ops[1].key)
+        if len(set(layer1 + layer2)) != 2 * (n - 1):
+            return None
+        return K, layer1, layer2
+
     def graph(self, mode: str) -> cgraph.CGraph:
         key = "fwd" if mode == "fwd" else mode
         if key not in self._graphs:
