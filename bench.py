@@ -373,7 +373,7 @@ def main():
         torch.cuda.synchronize(dev)
         flops_launch = runner.flops - f0           # real fp32-equivalent flops of all GEMMs of one step
         info = None
-    elif bound.chain_rank:
+    elif bound.chain_rank or bound.ladder:
         info = None
         # algorithmic flops: the plan compiler's pairwise count (= SURVEY 8(d) closed form for forward)
         flops_launch = bound.plan.program("train" if train else "fwd").flops_per_sample * B
@@ -424,7 +424,7 @@ def main():
         roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": achieved_tf / fp32_peak, "traffic": None,
                     "peak_source": "measured here: torch.matmul 8192^3 fp32 (TF32 off), best of 5",
-                    "kernel": "tnq_chain_kernel" if bound.chain_rank else "tnq_body_kernel",
+                    "kernel": "tnq_chain_kernel" if bound.chain_rank else ("tnq_ladder_kernel" if bound.ladder else "tnq_body_kernel"),
                     "flops_per_launch": flops_launch, "hbm": hbm}
         if info is not None:
             roofline.update({"tile_samples": info.tile_samples, "grid": info.grid,

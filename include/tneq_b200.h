@@ -97,6 +97,25 @@ int tnq_mps_chain(int K, int n, const float* const* cores, const float* const* s
                   float* const* grads, double log_scale, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * Warp-level sweep for TWO-LAYER merged MPS networks (QCTN.merge(mps_n, mps_n), reference
+ * tneq_qc/core/qctn.py:1296-1506; BASELINE cfg3), float32, edge rank K in {2,3}, n >= 3: the greedy
+ * sweep greedy_strategy.py:461-598 with its rank-6 environment kept in shared memory by the warp that
+ * owns the sample -- and for mode != 0 the loss engine_siamese.py:490-530 and the reverse sweep -- in
+ * one kernel (csrc/tnq_ladder.cu).
+ *   cores_a[q], cores_x[q], q < n-1 : first / second layer core on wires (q, q+1), [K][K][K][K]
+ *   states[q] : [K]     mx[q] : sample b at mx[q] + b * mx_stride[q], [K][K]
+ *   mode 0: values[B]      mode 1: values[B] (optional), *loss, grads_a[q], grads_x[q] (fused loss)
+ *   mode 2: grads seeded by seed[B] = d loss / d value (torch.autograd route)
+ * workspace: tnq_mps_ladder_workspace_bytes(K, n, B, mode) bytes (per-warp checkpoints and
+ * gradient slices; bounded by the number of resident warps, not by B).
+ */
+int64_t tnq_mps_ladder_workspace_bytes(int K, int n, int64_t B, int mode);
+int tnq_mps_ladder(int K, int n, const float* const* cores_a, const float* const* cores_x,
+                   const float* const* states, const float* const* mx, const int64_t* mx_stride, int64_t B, int mode,
+                   const float* seed, float* values, float* loss, float* const* grads_a, float* const* grads_x,
+                   double log_scale, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Large-bond-dimension regime: one pairwise contraction of the sweep as a batched GEMM on the
  * tcgen05 tensor cores with fp32-faithful 3xTF32 arithmetic (replaces the bmm that torch.einsum
  * dispatches for greedy_strategy.py:940,959 when the bond dimension is 64-128):

@@ -73,6 +73,10 @@ class _Bound:
         self.use_gemm_path = biggest > VM_MAX_CORE_ELEMS or os.environ.get("TNQ_FORCE_GEMM_PATH") == "1"
         self.chain_rank = 0 if (self.use_gemm_path or os.environ.get("TNQ_NO_CHAIN") == "1") else plan.mps_chain_rank()
         self._chain_ws = None
+        # two-layer merged MPS: warp-level ladder kernel (csrc/tnq_ladder.cu)
+        self.ladder = None
+        if not (self.use_gemm_path or self.chain_rank or os.environ.get("TNQ_NO_CHAIN") == "1"):
+            self.ladder = plan.mps_ladder()
         if self.use_gemm_path and plan.real_dtype != "f32":
             raise NotImplementedError("large-bond contraction runs on the tensor cores in float32 / complex64 only; "
                                       f"got {plan.dtype} with a core of {biggest} elements")
@@ -190,6 +194,47 @@ class _Call:
         gmap = dict(zip(order, grads))
         return values, (loss[0] if loss is not None else None), [gmap[k] for k in self.core_keys] if grads else []
 
+    # ---- two-layer merged MPS route: warp-level ladder kernel (csrc/tnq_ladder.cu) -------------
+    def _ladder(self, cores, mode, seed=None, log_scale=0.0):
+        from ctypes import c_void_p, c_int64
+        from .. import _lib
+        lib = _lib.load()
+        K, layer1, layer2 = self.bound.ladder
+        n, dev = self.bound.plan.nqubits, self.bound.device
+        by_key = dict(zip(self.core_keys, cores))
+        ca = [by_key[("core", k)] for k in layer1]
+        cx = [by_key[("core", k)] for k in layer2]
+        ca = [c if c.is_contiguous() else c.contiguous() for c in ca]
+        cx = [c if c.is_contiguous() else c.contiguous() for c in cx]
+        sts = [t if t.is_contiguous() else t.contiguous() for t in (self.states[q] for q in range(n))]
+        ms, strides = [], []
+        for q in range(n):
+            m = self.mxs[q]
+            st = m.stride()
+            if st[-1] != 1 or st[-2] != K:
+                m = m.contiguous()
+                st = m.stride()
+            ms.append(m)
+            strides.append(0 if (m.shape[0] == 1 and self.B != 1) else st[0])
+        ws_bytes = int(lib.tnq_mps_ladder_workspace_bytes(K, n, self.B, mode))
+        if self.bound._chain_ws is None or self.bound._chain_ws.numel() < ws_bytes:
+            self.bound._chain_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        values = torch.empty(self.B, dtype=torch.float32, device=dev) if mode != 2 else None
+        loss = torch.empty(1, dtype=torch.float32, device=dev) if mode == 1 else None
+        ga = [torch.empty_like(c) for c in ca] if mode != 0 else []
+        gx = [torch.empty_like(c) for c in cx] if mode != 0 else []
+        arr = lambda ts: (c_void_p * max(1, len(ts)))(*[t.data_ptr() for t in ts])
+        with torch.cuda.device(dev):
+            _lib.check(lib.tnq_mps_ladder(K, n, arr(ca), arr(cx), arr(sts), arr(ms), (c_int64 * n)(*strides), self.B, mode,
+                                          c_void_p(seed.data_ptr()) if seed is not None else None,
+                                          c_void_p(values.data_ptr()) if values is not None else None,
+                                          c_void_p(loss.data_ptr()) if loss is not None else None,
+                                          arr(ga) if ga else None, arr(gx) if gx else None, float(log_scale),
+                                          c_void_p(self.bound._chain_ws.data_ptr()), self.bound._chain_ws.numel(),
+                                          c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        gmap = {("core", k): g for k, g in zip(layer1 + layer2, ga + gx)}
+        return values, (loss[0] if loss is not None else None), [gmap[k] for k in self.core_keys] if ga else []
+
     # ---- large-bond route: node-by-node on the tcgen05 GEMM path ------------------------------
     def _gemm_inputs(self, cores):
         out = {}
@@ -224,6 +269,8 @@ class _Call:
     def forward(self, cores):
         if self.bound.chain_rank:
             return self._chain(cores, 0)[0]
+        if self.bound.ladder:
+            return self._ladder(cores, 0)[0]
         if self.bound.use_gemm_path:
             return self._gemm_forward(cores)
         prog = self.bound.program("fwd")
@@ -233,6 +280,8 @@ class _Call:
     def backward(self, cores, grad_out):
         if self.bound.chain_rank:
             return self._chain(cores, 2, seed=grad_out.reshape(-1).to(torch.float32).contiguous())[2]
+        if self.bound.ladder:
+            return self._ladder(cores, 2, seed=grad_out.reshape(-1).to(torch.float32).contiguous())[2]
         if self.bound.use_gemm_path:
             seed = _real_view(grad_out.contiguous()).reshape(self.nsamples, -1).to(torch.float32).contiguous()
             return self._gemm_backward(cores, seed)[0]
@@ -255,6 +304,9 @@ class _Call:
         """Fused forward + loss + reverse sweep.  Returns (loss, grads, values)."""
         if self.bound.chain_rank:
             values, loss, grads = self._chain(cores, 1, log_scale=log_scale)
+            return loss, grads, values
+        if self.bound.ladder:
+            values, loss, grads = self._ladder(cores, 1, log_scale=log_scale)
             return loss, grads, values
         if self.bound.use_gemm_path:
             # forward nodes, then the loss seed from the forward result (element-wise, torch), then the

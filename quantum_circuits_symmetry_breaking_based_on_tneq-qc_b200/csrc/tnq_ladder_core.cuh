@@ -35,10 +35,12 @@
 #include <stdint.h>
 
 #ifdef __CUDACC__
+#define TNQ_HOSTDEV __host__ __device__
 #define TNQ_HD __device__ __forceinline__
 #define TNQ_UNROLL _Pragma("unroll")
 #define TNQ_NOUNROLL _Pragma("unroll 1")
 #else
+#define TNQ_HOSTDEV
 #define TNQ_HD inline
 #define TNQ_UNROLL
 #define TNQ_NOUNROLL
@@ -79,8 +81,8 @@ struct Dims {
     static_assert(SPW * SST >= K4 * LP, "environment buffer doubles as the lane-reduction scratch");
     static_assert(USZ >= K4, "U buffer doubles as the X-gradient side buffer");
     // per-warp gradient slice: [q][K4] dX_q | [q][K3] dBs_q (q >= 1) | [K2] dAs0
-    static constexpr int ckpt_floats(int n) { return (n - 2) * (E_SZ + K2 * 32); }
-    static constexpr int grad_floats(int n) { return (n - 1) * K4 + (n - 1) * K3 + K2; }
+    TNQ_HOSTDEV static constexpr int ckpt_floats(int n) { return (n - 2) * (E_SZ + K2 * 32); }
+    TNQ_HOSTDEV static constexpr int grad_floats(int n) { return (n - 1) * K4 + (n - 1) * K3 + K2; }
 };
 
 struct Args {

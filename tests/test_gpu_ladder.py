@@ -1,0 +1,131 @@
+"""GPU parity of the warp-level ladder kernel (csrc/tnq_ladder.cu): two-layer merged MPS networks
+(BASELINE cfg3) through the engine API and the C ABI, against the oracle at sizes the oracle
+finishes in seconds, against the generic contraction VM (an independent CUDA implementation of the
+same plan), and -- at cfg3's full size -- through size-independent properties.
+Tolerance: 1e-5 relative (north_star) on well-conditioned samples, float64 oracle as yardstick.
+"""
+import os
+
+import pytest
+import torch
+
+import tneq_b200
+from oracle import qctn_oracle as oc
+from helpers import make_case, well_conditioned_case, upcast, clone_mx, rel_err, elem_rel_err
+
+pytestmark = pytest.mark.gpu
+H = tneq_b200.QCTNHelper
+DEV = "cuda:0"
+
+
+def merged_graph(n, K):
+    q = tneq_b200.QCTN(H.generate_example_graph(n=n, graph_type="mps", dim_char=str(K)))
+    return tneq_b200.QCTN.merge(q, q).graph
+
+
+def _to_dev(x):
+    if isinstance(x, oc.TNT):
+        return tneq_b200.TNTensor(x.tensor.to(DEV), x.scale, x.log_scale)
+    return x.to(DEV)
+
+
+def _setup(graph, K, cores):
+    be = tneq_b200.BackendFactory.create_backend("b200", device=DEV, dtype="float32")
+    eng = tneq_b200.EngineSiamese(backend=be, strategy_mode="balanced", mx_K=K)
+    q = tneq_b200.QCTN(graph, backend=be)
+    for k, v in cores.items():
+        q.cores_weights[k] = v.to(DEV).requires_grad_(True)
+    return eng, q
+
+
+def _bound(eng, q, st, mx):
+    return next(iter(eng._compiled(q, st, mx, True, "symmetric").plans.values()))
+
+
+@pytest.mark.parametrize("n,K,B", [(3, 3, 4), (5, 3, 100), (24, 3, 50), (9, 2, 333), (24, 2, 64)])
+def test_ladder_vs_oracle(n, K, B, built_lib):
+    graph = merged_graph(n, K)
+    names, table, nq, cores, states, mxs = well_conditioned_case(graph, K, B, "float32", seed=n + K)
+    want = oc.forward(graph, cores, states, clone_mx(mxs))
+    c64 = {k: v.double() for k, v in cores.items()}
+    s64 = [s.double() for s in states]
+    truth = oc.forward(graph, c64, s64, [upcast(m, torch.float64) for m in clone_mx(mxs)])
+    eng, q = _setup(graph, K, cores)
+    st = [s.to(DEV) for s in states]
+    got = eng.contract_with_compiled_strategy(q, st, [_to_dev(m) for m in clone_mx(mxs)])
+    assert _bound(eng, q, st, [_to_dev(m) for m in clone_mx(mxs)]).ladder is not None
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert elem_rel_err(got.double(), truth) < max(1e-5, 3 * elem_rel_err(want.double(), truth))
+    wl, wg = oc.loss_and_grads(graph, cores, states, clone_mx(mxs))
+    tl, tg = oc.loss_and_grads(graph, c64, s64, [upcast(m, torch.float64) for m in clone_mx(mxs)])
+    for fused in (True, False):   # fused loss kernel (mode 1), then the torch.autograd route (modes 0 + 2)
+        loss, grads = eng.contract_with_compiled_strategy_for_gradient(q, st, [_to_dev(m) for m in clone_mx(mxs)],
+                                                                       fused=fused)
+        assert abs(loss.item() - tl.item()) <= max(1e-5 * abs(tl.item()), 3 * abs(wl.item() - tl.item()))
+        assert len(grads) == len(wg)
+        for g, w, t in zip(grads, wg, tg):
+            assert g.shape == w.shape and g.dtype == w.dtype
+            assert rel_err(g.double(), t) < max(1e-5, 3 * rel_err(w.double(), t)), fused
+
+
+def test_ladder_vs_vm_route(built_lib):
+    """The generic contraction VM runs the same plan with different kernels and association order."""
+    n, K, B = 24, 3, 1000
+    graph = merged_graph(n, K)
+    names, table, nq, cores, states, mxs = make_case(graph, K, B, "float32", seed=7)
+    st = [s.to(DEV) for s in states]
+    out = {}
+    for route in ("ladder", "vm"):
+        if route == "vm":
+            os.environ["TNQ_NO_CHAIN"] = "1"
+        try:
+            eng, q = _setup(graph, K, cores)
+            vals = eng.contract_with_compiled_strategy(q, st, [_to_dev(m) for m in clone_mx(mxs)])
+            assert (_bound(eng, q, st, [_to_dev(m) for m in clone_mx(mxs)]).ladder is not None) == (route == "ladder")
+            loss, grads = eng.contract_with_compiled_strategy_for_gradient(q, st, [_to_dev(m) for m in clone_mx(mxs)])
+            out[route] = (vals.cpu(), loss.item(), [g.cpu() for g in grads])
+        finally:
+            os.environ.pop("TNQ_NO_CHAIN", None)
+    va, la, ga = out["ladder"]
+    vb, lb, gb = out["vm"]
+    big = vb.abs() > 1e-3 * vb.abs().max()           # samples that did not cancel in float32
+    assert ((va - vb).abs()[big] / vb.abs()[big]).max() < 2e-4
+    assert rel_err(va, vb) < 1e-5
+    assert abs(la - lb) < 1e-4 * abs(lb)
+
+
+def test_cfg3_full_size_properties(built_lib):
+    """cfg3 size (24 qubits, batch 16384): normalisation known answer, ragged batches, and the
+    loss / gradient of a batch equal to the sample-weighted mean over its two halves."""
+    n, K, B = 24, 3, 16384
+    graph = merged_graph(n, K)
+    torch.manual_seed(11)
+    names, table, nq = oc.parse_graph(graph)
+    cores = oc.random_cores(table, torch.float32)
+    states = [s.to(DEV) for s in oc.unit_states(nq, K)]
+    eng, q = _setup(graph, K, cores)
+    # KAT-1: orthogonal cores + identity measurements => 1 for every sample
+    eye = [torch.eye(K, device=DEV).expand(B, K, K).contiguous() for _ in range(nq)]
+    got = eng.contract_with_compiled_strategy(q, states, eye)
+    assert got.shape == (B,)
+    assert (got - 1).abs().max().item() < 1e-5
+    # random data: the batch against its two (ragged) halves
+    x = torch.randn(B, nq, device=DEV)
+    mx, _ = eng.generate_data(x, K=K, ret_type="tensor")
+    mx = [m.contiguous() * 3.0 for m in mx]           # keep typical values away from the 1e-10 clamp
+    full = eng.contract_with_compiled_strategy(q, states, mx)
+    cut = 7001
+    a = eng.contract_with_compiled_strategy(q, states, [m[:cut] for m in mx])
+    b = eng.contract_with_compiled_strategy(q, states, [m[cut:] for m in mx])
+    assert torch.equal(full, torch.cat([a, b]))       # per-sample arithmetic does not depend on the batch
+    lf, gf = eng.contract_with_compiled_strategy_for_gradient(q, states, mx)
+    la, ga = eng.contract_with_compiled_strategy_for_gradient(q, states, [m[:cut] for m in mx])
+    lb, gb = eng.contract_with_compiled_strategy_for_gradient(q, states, [m[cut:] for m in mx])
+    wa, wb = cut / B, (B - cut) / B
+    assert abs(lf.item() - (wa * la.item() + wb * lb.item())) < 1e-5 * abs(lf.item())
+    for f, u, v in zip(gf, ga, gb):
+        mix = wa * u + wb * v
+        assert (f - mix).abs().max().item() <= 2e-4 * mix.abs().max().item() + 1e-7
+    # determinism: the same launch twice gives bit-identical gradients
+    lf2, gf2 = eng.contract_with_compiled_strategy_for_gradient(q, states, mx)
+    assert lf.item() == lf2.item() and all(torch.equal(u, v) for u, v in zip(gf, gf2))
