@@ -24,7 +24,7 @@ namespace {
 using namespace tnq_ladder;
 
 constexpr int WARPS_FWD = 12;     // warps per CTA, forward only (one CTA per SM)
-constexpr int WARPS_TRAIN = 9;    // warps per CTA with the reverse sweep (shared memory bound)
+constexpr int WARPS_TRAIN = 8;    // with the reverse sweep: registers are allocated in units of 4 warps (8 x 32 x 255 <= 64 K)
 
 template <int K>
 __host__ __device__ constexpr int cst_floats(int n) {
@@ -32,7 +32,7 @@ __host__ __device__ constexpr int cst_floats(int n) {
 }
 
 template <int K, int MODE>
-__global__ void __maxnreg__(MODE == 0 ? 168 : 224)
+__global__ void __maxnreg__(MODE == 0 ? 168 : 255)
 tnq_ladder_kernel(const __grid_constant__ Args a, long long B, long long ngroups, const float* __restrict__ seed,
                   float* __restrict__ values, float* __restrict__ gparts, float* __restrict__ lparts,
                   float* __restrict__ ckpt, float log_scale, float inv_count) {
@@ -125,7 +125,7 @@ tnq_ladder_finalize_kernel(const __grid_constant__ Args a, const float* __restri
         if (q == 0) return;                        // slot unused: A_0 is folded with both states (below)
         const int cc = r / D::K2, ee = (r / K) % K, f = r % K;
         for (int d = 0; d < K; ++d) a.gradA[q][((cc * K + d) * K + ee) * K + f] = s * __ldg(a.state[q + 1] + d);
-    } else {
+    } else if (e < nX + nB + D::K2) {                // (the slice is padded to a multiple of 4 floats)
         const int ef = e - nX - nB;
         for (int cc = 0; cc < K; ++cc)
             for (int d = 0; d < K; ++d)

@@ -81,8 +81,9 @@ struct Dims {
     static_assert(SPW * SST >= K4 * LP, "environment buffer doubles as the lane-reduction scratch");
     static_assert(USZ >= K4, "U buffer doubles as the X-gradient side buffer");
     // per-warp gradient slice: [q][K4] dX_q | [q][K3] dBs_q (q >= 1) | [K2] dAs0
-    TNQ_HOSTDEV static constexpr int ckpt_floats(int n) { return (n - 2) * (E_SZ + K2 * 32); }
-    TNQ_HOSTDEV static constexpr int grad_floats(int n) { return (n - 1) * K4 + (n - 1) * K3 + K2; }
+    // (padded to a multiple of 4 floats so that everything behind it stays 16-byte aligned)
+    TNQ_HOSTDEV static constexpr int ckpt_floats(int n) { return (n - 2) * (E_SZ + T2_SZ); }
+    TNQ_HOSTDEV static constexpr int grad_floats(int n) { return ((n - 1) * K4 + (n - 1) * K3 + K2 + 3) / 4 * 4; }
 };
 
 struct Args {
@@ -111,7 +112,7 @@ struct WarpCtx {
     float *E, *U, *T2, *M, *V;  // per-warp buffers (shared memory)
     float *D, *dT2;             // training only
     float* ckE;                 // per-warp checkpoints (global): [q-1][E_SZ]
-    float* ckT2;                //                                [q-1][K2][32]
+    float* ckT2;                //                                [q-1][T2_SZ]
     float* gpart;               // per-warp gradient slice (global)
     const Args* args;
     long long B;
@@ -178,7 +179,7 @@ TNQ_HD float load_m(const WarpCtx<K>& c, int q, long long b, int it) {
 
 // ---- phase A: E -> T2 (item = (p,g)) -------------------------------------------------------
 template <int K>
-TNQ_HD void phase_a_fwd(const WarpCtx<K>& c, int lane, const float* Bs, float* ckT2) {
+TNQ_HD void phase_a_fwd(const WarpCtx<K>& c, int lane, const float* Bs) {
     using D = Dims<K>;
     const int s = lane / D::IPS, it = lane % D::IPS, p = it / K, g = it % K;
     const float* e = c.E + s * D::SST + p * D::K2 + g;
@@ -231,10 +232,7 @@ TNQ_HD void phase_a_fwd(const WarpCtx<K>& c, int lane, const float* Bs, float* c
     TNQ_UNROLL
     for (int f = 0; f < K; ++f)
         TNQ_UNROLL
-        for (int o = 0; o < K; ++o) {
-            t2[(f * K + o) * D::K2] = T2[f][o];
-            if (ckT2 != nullptr) ckT2[(f * K + o) * 32 + lane] = T2[f][o];
-        }
+        for (int o = 0; o < K; ++o) t2[(f * K + o) * D::K2] = T2[f][o];
 }
 
 // ---- phase B: U[i][q][r][p] = sum_k M[i][k] X[p][q][k][r] (item = (q,r)) ---------------------
@@ -678,6 +676,16 @@ TNQ_HD void first_a_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const f
     }
 }
 
+// += into the warp's own gradient slice: a reduction without return value on the device (no load
+// latency on the critical path; the address has a single writer, so the order of adds is fixed)
+TNQ_HD void gadd(float* p, float v) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+
 // ---- lane reduction: scratch[v][lane] then row sums in lane order -> += gp[v] ---------------------
 template <int K, int NV>
 TNQ_HD void flush_put(float* scr, int lane, const float* acc) {
@@ -697,16 +705,52 @@ TNQ_HD void flush_sum(const float* scr, const float* xr, int lane, float* gp) {
             TNQ_UNROLL
             for (int s = 0; s < D::SPW; ++s) t += xr[s * D::USZ + v];
         }
-        gp[v] += t;
+        gadd(gp + v, t);
     }
 }
 
-// cooperative copies between the warp's E buffer and its global checkpoint
-template <int K>
-TNQ_HD void copy_lanes(float* dst, const float* src, int lane) {
-    using D = Dims<K>;
-    TNQ_NOUNROLL
-    for (int i = lane; i < D::SPW * D::SST; i += 32) dst[i] = src[i];
+// ---- checkpoints: cooperative 16-byte copies between a warp's buffers and global memory -----------
+// store: shared -> global (fire and forget).  load: global -> shared with cp.async on the device,
+// completed by ckpt_wait<PENDING>() (all but the PENDING most recently committed groups) followed
+// by the phase's __syncwarp(); the CPU emulation copies at issue time.
+template <int NFLOATS>
+TNQ_HD void ckpt_store(float* dst, const float* src, int lane) {
+    static_assert(NFLOATS % 4 == 0, "16-byte units");
+#ifdef __CUDA_ARCH__
+    TNQ_UNROLL
+    for (int i = 0; i < (NFLOATS / 4 + 31) / 32; ++i) {
+        const int j = lane + 32 * i;
+        if (j < NFLOATS / 4) reinterpret_cast<float4*>(dst)[j] = reinterpret_cast<const float4*>(src)[j];
+    }
+#else
+    for (int i = lane; i < NFLOATS; i += 32) dst[i] = src[i];
+#endif
+}
+template <int NFLOATS>
+TNQ_HD void ckpt_load_async(float* dst, const float* src, int lane) {
+    static_assert(NFLOATS % 4 == 0, "16-byte units");
+#ifdef __CUDA_ARCH__
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    TNQ_UNROLL
+    for (int i = 0; i < (NFLOATS / 4 + 31) / 32; ++i) {
+        const int j = lane + 32 * i;
+        if (j < NFLOATS / 4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * j), "l"(src + 4 * j) : "memory");
+    }
+#else
+    for (int i = lane; i < NFLOATS; i += 32) dst[i] = src[i];
+#endif
+}
+TNQ_HD void ckpt_commit() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int PENDING>
+TNQ_HD void ckpt_wait() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+#endif
 }
 
 }  // namespace tnq_ladder
@@ -760,14 +804,16 @@ TNQ_HD void ladder_group(const WarpCtx<K>& c, TNQ_LANES_PARAM, long long b0) {
     TNQ_PHASE(if (TNQ_ACTIVE) phase_c_fwd<K>(c, lane, TNQ_XT(0));)
     for (int q = 1; q <= n - 2; ++q) {
         TNQ_PHASE(
-            if (CK) copy_lanes<K>(c.ckE + (size_t)(q - 1) * D::E_SZ, c.E, lane);
+            if (CK && q < n - 2) ckpt_store<D::E_SZ>(c.ckE + (size_t)(q - 1) * D::E_SZ, c.E, lane);
             if (TNQ_ACTIVE) {
                 c.M[lane] = st.mnext;
                 st.mnext = load_m<K>(c, q + 1, b0 + TNQ_S, TNQ_IT);
-                phase_a_fwd<K>(c, lane, TNQ_BS(q), CK ? c.ckT2 + (size_t)(q - 1) * D::K2 * 32 : nullptr);
+                phase_a_fwd<K>(c, lane, TNQ_BS(q));
             })
         if (q < n - 2) {
-            TNQ_PHASE(if (TNQ_ACTIVE) phase_b<K>(c, lane, TNQ_XN(q));)
+            TNQ_PHASE(
+                if (CK) ckpt_store<D::T2_SZ>(c.ckT2 + (size_t)(q - 1) * D::T2_SZ, c.T2, lane);
+                if (TNQ_ACTIVE) phase_b<K>(c, lane, TNQ_XN(q));)
             TNQ_PHASE(if (TNQ_ACTIVE) phase_c_fwd<K>(c, lane, TNQ_XT(q));)
         }
     }
@@ -818,29 +864,39 @@ TNQ_HD void ladder_group(const WarpCtx<K>& c, TNQ_LANES_PARAM, long long b0) {
         last_bwd<K>(c, st, lane, TNQ_XN(n - 2));
         flush_put<K, D::K4>(c.D, lane, st.accX);
     })
-    TNQ_PHASE(flush_sum<K, D::K4, false>(c.D, nullptr, lane, TNQ_GX(n - 2));)
+    // cp.async groups are committed alternately: T2 of the next step (after this step's last use of
+    // the T2 buffer), then E of that step (at its start); every wait leaves the newest group pending
+    TNQ_PHASE(
+        flush_sum<K, D::K4, false>(c.D, nullptr, lane, TNQ_GX(n - 2));
+        if (n - 3 >= 1) ckpt_load_async<D::T2_SZ>(c.T2, c.ckT2 + (size_t)(n - 4) * D::T2_SZ, lane);
+        ckpt_commit();)
     for (int q = n - 2; q >= 1; --q) {
         if (q < n - 2) {
             TNQ_PHASE(
-                copy_lanes<K>(c.E, c.ckE + (size_t)(q - 1) * D::E_SZ, lane);
+                ckpt_load_async<D::E_SZ>(c.E, c.ckE + (size_t)(q - 1) * D::E_SZ, lane);
+                ckpt_commit();
                 if (TNQ_ACTIVE) {
-                    const float* ck = c.ckT2 + (size_t)(q - 1) * D::K2 * 32;
-                    const int g = TNQ_IT % K, p = TNQ_IT / K;
-                    TNQ_UNROLL
-                    for (int fo = 0; fo < D::K2; ++fo) c.T2[TNQ_S * D::K4 + fo * D::K2 + g * K + p] = ck[fo * 32 + lane];
                     c.M[lane] = st.mnext;
                     st.mnext = load_m<K>(c, q - 1, b0 + TNQ_S, TNQ_IT);
                 })
-            TNQ_PHASE(if (TNQ_ACTIVE) phase_b<K>(c, lane, TNQ_XN(q));)
+            TNQ_PHASE(
+                if (TNQ_ACTIVE) phase_b<K>(c, lane, TNQ_XN(q));
+                ckpt_wait<1>();)                                  // T2_q has landed
             TNQ_PHASE(if (TNQ_ACTIVE) phase_c_bwd<K>(c, st, lane, TNQ_XT(q));)
             TNQ_PHASE(if (TNQ_ACTIVE) phase_du<K>(c, lane);)
-            TNQ_PHASE(if (TNQ_ACTIVE) flush_put<K, D::K4>(c.D, lane, st.accX);)
-            TNQ_PHASE(flush_sum<K, D::K4, true>(c.D, c.U, lane, TNQ_GX(q));)
+            TNQ_PHASE(
+                if (TNQ_ACTIVE) flush_put<K, D::K4>(c.D, lane, st.accX);
+                if (q - 1 >= 1) ckpt_load_async<D::T2_SZ>(c.T2, c.ckT2 + (size_t)(q - 2) * D::T2_SZ, lane);
+                ckpt_commit();)
+            TNQ_PHASE(
+                flush_sum<K, D::K4, true>(c.D, c.U, lane, TNQ_GX(q));
+                ckpt_wait<1>();)                                  // E_q has landed
         }
         TNQ_PHASE(if (TNQ_ACTIVE) phase_a_bwd<K>(c, st, lane, TNQ_BS(q));)
         TNQ_PHASE(if (TNQ_ACTIVE) flush_put<K, D::K3>(c.E, lane, st.accB);)
         TNQ_PHASE(flush_sum<K, D::K3, false>(c.E, nullptr, lane, TNQ_GB(q));)
     }
+    TNQ_PHASE(ckpt_wait<0>();)
     // first step
     TNQ_PHASE(if (TNQ_ACTIVE) {
         c.M[lane] = st.mnext;
