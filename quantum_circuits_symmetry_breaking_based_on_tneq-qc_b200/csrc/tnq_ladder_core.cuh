@@ -61,15 +61,21 @@ struct Dims {
     // (K = 3) or at most 2-way (K = 2)
     static constexpr int PITCH = K == 3 ? 85 : 16;
     static constexpr int SST = K == 3 ? 765 : 67;
-    static constexpr int UP = K == 3 ? 4 : K;   // padded extent of U's innermost index p
-    static constexpr int USZ = K3 * UP;
+    // U is kept in one of two layouts: [i][qr][p padded to UP] (reverse sweep) or
+    // [i][p][qr padded to UQ] (forward sweep, where (q,r) is the packed-FMA vector index)
+    static constexpr int UP = 4;
+    static constexpr int UQ = (K2 + 3) / 4 * 4;
+    static constexpr int USZ = K3 * UP > K2 * UQ ? K3 * UP : K2 * UQ;
     static constexpr int XTP = (K2 + 3) / 4 * 4;  // padded (g,i) vector of the transposed core
-    static constexpr int BSP = K == 3 ? 4 : K;  // padded innermost extent of Bs
+    static constexpr int BSP = 4;               // padded innermost extent of Bs
     static constexpr int LP = LANES | 1;        // row pitch of the lane-reduction scratch
-    // per-step block of the constant pool: X natural | X transposed [h][j][(g,i)] | Bs [c][e][f]
+    // per-step block of the constant pool: X natural | X transposed [h][j][(g,i)] | Bs [c][e][f] |
+    // Bs transposed [f][(c,e)]
     // (each part starts on a 16-byte boundary)
+    static constexpr int BTP = (K2 + 3) / 4 * 4;  // padded (l,n) vector of the transposed Bs
     static constexpr int OFF_XN = 0, OFF_XT = (K4 + 3) / 4 * 4, OFF_BS = OFF_XT + K2 * XTP;
-    static constexpr int CSTEP = (OFF_BS + K2 * BSP + 3) / 4 * 4;
+    static constexpr int OFF_BT = (OFF_BS + K2 * BSP + 3) / 4 * 4;     // BsT[o][(l,n)]
+    static constexpr int CSTEP = (OFF_BT + K * BTP + 3) / 4 * 4;
     // per-warp shared-memory buffers (floats, every offset a multiple of 4)
     static constexpr int E_SZ = (SPW * SST + 3) / 4 * 4;
     static constexpr int U_SZ = SPW * USZ;
@@ -97,10 +103,88 @@ struct Args {
     int n;
 };
 
+// ---- packed fp32 arithmetic ---------------------------------------------------------------------
+// On sm_100 a plain FFMA issues every second cycle per scheduler (measured: 38.9 TFLOP/s over 148
+// SMs, scratch/ffma_rate.cu); only the packed form fma.rn.f32x2 (SASS FFMA2: two independent fp32
+// FMAs on an aligned register pair, scalar operands broadcast for free) reaches the fp32 peak.  All
+// hot loops below are therefore "vector += scalar * vector" over Vec<N> = N/2 register pairs (+ one
+// plain float when N is odd).  Each half is an ordinary IEEE fma: the CPU emulation uses fmaf twice.
+struct F2 {
+    float lo, hi;
+};
+TNQ_HD F2 fma2(F2 a, F2 b, F2 c) {
+#ifdef __CUDA_ARCH__
+    unsigned long long A, B, C, R;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a.lo), "f"(a.hi));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b.lo), "f"(b.hi));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(C) : "f"(c.lo), "f"(c.hi));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(R) : "l"(A), "l"(B), "l"(C));
+    F2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.lo), "=f"(r.hi) : "l"(R));
+    return r;
+#else
+    return F2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)};
+#endif
+}
+TNQ_HD F2 fma2(F2 a, float s, F2 c) { return fma2(a, F2{s, s}, c); }
+
+template <int N>
+struct Vec {
+    static constexpr int NP = N / 2;
+    F2 p[NP > 0 ? NP : 1];
+    float s;                    // element N-1 when N is odd
+    // i must be a compile-time constant after unrolling
+    TNQ_HD float get(int i) const { return i < 2 * NP ? ((i & 1) ? p[i >> 1].hi : p[i >> 1].lo) : s; }
+    TNQ_HD void set(int i, float v) {
+        if (i < 2 * NP) {
+            if (i & 1) p[i >> 1].hi = v; else p[i >> 1].lo = v;
+        } else {
+            s = v;
+        }
+    }
+    TNQ_HD void zero() {
+        TNQ_UNROLL
+        for (int i = 0; i < NP; ++i) p[i] = F2{0.f, 0.f};
+        s = 0.f;
+    }
+};
+// acc += s * x
+template <int N>
+TNQ_HD void axpy(Vec<N>& acc, float s, const Vec<N>& x) {
+    TNQ_UNROLL
+    for (int i = 0; i < Vec<N>::NP; ++i) acc.p[i] = fma2(x.p[i], s, acc.p[i]);
+    if (N & 1) acc.s = fmaf(x.s, s, acc.s);
+}
+// init + sum_i a[i] * b[i]
+template <int N>
+TNQ_HD float dot(const Vec<N>& a, const Vec<N>& b, float init) {
+    F2 t{init, 0.f};
+    TNQ_UNROLL
+    for (int i = 0; i < Vec<N>::NP; ++i) t = fma2(a.p[i], b.p[i], t);
+    if (N & 1) t.lo = fmaf(a.s, b.s, t.lo);
+    return t.lo + t.hi;
+}
+// N consecutive floats (padded to a multiple of 4, 16-byte aligned) from shared memory
+template <int N>
+TNQ_HD void vload(Vec<N>& v, const float* p) {
+    float t[(N + 3) / 4 * 4];
+#ifdef __CUDA_ARCH__
+    TNQ_UNROLL
+    for (int i = 0; i < (N + 3) / 4; ++i) {
+        const float4 q = *reinterpret_cast<const float4*>(p + 4 * i);
+        t[4 * i] = q.x, t[4 * i + 1] = q.y, t[4 * i + 2] = q.z, t[4 * i + 3] = q.w;
+    }
+#else
+    for (int i = 0; i < (N + 3) / 4 * 4; ++i) t[i] = p[i];
+#endif
+    TNQ_UNROLL
+    for (int i = 0; i < N; ++i) v.set(i, t[i]);
+}
+
 template <int K>
 struct LaneState {
-    float accX[Dims<K>::K4];    // this lane's partial d loss / d X_q
-    float accB[Dims<K>::K3];    // this lane's partial d loss / d Bs_q (or dAs0 in its first K2 entries)
+    Vec<Dims<K>::K2> accX[Dims<K>::K2];  // this lane's partial d loss / d X_q: [g*K+i] over (h,j)
+    Vec<K> accB[Dims<K>::K2];   // this lane's partial d loss / d Bs_q: [c*K+e] over f (or dAs0: [e] over f)
     float pf[Dims<K>::K2];      // last step: P_fo[i][p], later d P[i][p]
     float mnext;                // prefetched measurement-matrix element of the next step
     float loss;                 // running loss contribution (lanes with item 0)
@@ -178,27 +262,25 @@ TNQ_HD float load_m(const WarpCtx<K>& c, int q, long long b, int it) {
 }
 
 // ---- phase A: E -> T2 (item = (p,g)) -------------------------------------------------------
+// this item's K^4 slice of E as K^2 vectors over (l,n)
 template <int K>
-TNQ_HD void phase_a_fwd(const WarpCtx<K>& c, int lane, const float* Bs) {
+TNQ_HD void gather_epg(const float* e, Vec<Dims<K>::K2> (&Epg)[K][K]) {
     using D = Dims<K>;
-    const int s = lane / D::IPS, it = lane % D::IPS, p = it / K, g = it % K;
-    const float* e = c.E + s * D::SST + p * D::K2 + g;
-    float Epg[K][K][K][K];   // [c][l][n][e]
     TNQ_UNROLL
     for (int cc = 0; cc < K; ++cc)
         TNQ_UNROLL
-        for (int l = 0; l < K; ++l)
+        for (int ee = 0; ee < K; ++ee)
             TNQ_UNROLL
-            for (int n = 0; n < K; ++n)
+            for (int l = 0; l < K; ++l)
                 TNQ_UNROLL
-                for (int ee = 0; ee < K; ++ee) Epg[cc][l][n][ee] = e[(cc * K + l) * D::PITCH + n * D::K3 + ee * K];
-    float T1[K][K][K];       // [f][l][n]
+                for (int n = 0; n < K; ++n) Epg[cc][ee].set(l * K + n, e[(cc * K + l) * D::PITCH + n * D::K3 + ee * K]);
+}
+// T1[f][(l,n)] = sum_{c,e} Bs[c][e][f] Epg[c][e][(l,n)]
+template <int K>
+TNQ_HD void contract_t1(const float* Bs, const Vec<Dims<K>::K2> (&Epg)[K][K], Vec<Dims<K>::K2> (&T1)[K]) {
+    using D = Dims<K>;
     TNQ_UNROLL
-    for (int f = 0; f < K; ++f)
-        TNQ_UNROLL
-        for (int l = 0; l < K; ++l)
-            TNQ_UNROLL
-            for (int n = 0; n < K; ++n) T1[f][l][n] = 0.f;
+    for (int f = 0; f < K; ++f) T1[f].zero();
     TNQ_UNROLL
     for (int cc = 0; cc < K; ++cc)
         TNQ_UNROLL
@@ -206,37 +288,37 @@ TNQ_HD void phase_a_fwd(const WarpCtx<K>& c, int lane, const float* Bs) {
             float bs[D::BSP];
             ldv<D::BSP>(Bs + (cc * K + ee) * D::BSP, bs);
             TNQ_UNROLL
-            for (int l = 0; l < K; ++l)
-                TNQ_UNROLL
-                for (int n = 0; n < K; ++n)
-                    TNQ_UNROLL
-                    for (int f = 0; f < K; ++f) T1[f][l][n] = fmaf(bs[f], Epg[cc][l][n][ee], T1[f][l][n]);
+            for (int f = 0; f < K; ++f) axpy(T1[f], bs[f], Epg[cc][ee]);
         }
-    float T2[K][K];          // [f][o]
+}
+
+template <int K>
+TNQ_HD void phase_a_fwd(const WarpCtx<K>& c, int lane, const float* Bs) {
+    using D = Dims<K>;
+    const int s = lane / D::IPS, it = lane % D::IPS, p = it / K, g = it % K;
+    Vec<D::K2> Epg[K][K], T1[K];
+    gather_epg<K>(c.E + s * D::SST + p * D::K2 + g, Epg);
+    contract_t1<K>(Bs, Epg, T1);
+    Vec<K> T2[K];            // [f] over o
     TNQ_UNROLL
-    for (int f = 0; f < K; ++f)
-        TNQ_UNROLL
-        for (int o = 0; o < K; ++o) T2[f][o] = 0.f;
+    for (int f = 0; f < K; ++f) T2[f].zero();
     TNQ_UNROLL
-    for (int l = 0; l < K; ++l)
+    for (int ln = 0; ln < D::K2; ++ln) {
+        Vec<K> bs;
+        vload<K>(bs, Bs + ln * D::BSP);
         TNQ_UNROLL
-        for (int n = 0; n < K; ++n) {
-            float bs[D::BSP];
-            ldv<D::BSP>(Bs + (l * K + n) * D::BSP, bs);
-            TNQ_UNROLL
-            for (int f = 0; f < K; ++f)
-                TNQ_UNROLL
-                for (int o = 0; o < K; ++o) T2[f][o] = fmaf(T1[f][l][n], bs[o], T2[f][o]);
-        }
+        for (int f = 0; f < K; ++f) axpy(T2[f], T1[f].get(ln), bs);
+    }
     float* t2 = c.T2 + s * D::K4 + g * K + p;
     TNQ_UNROLL
     for (int f = 0; f < K; ++f)
         TNQ_UNROLL
-        for (int o = 0; o < K; ++o) t2[(f * K + o) * D::K2] = T2[f][o];
+        for (int o = 0; o < K; ++o) t2[(f * K + o) * D::K2] = T2[f].get(o);
 }
 
-// ---- phase B: U[i][q][r][p] = sum_k M[i][k] X[p][q][k][r] (item = (q,r)) ---------------------
-template <int K>
+// ---- phase B: U[i][p][q][r] = sum_k M[i][k] X[p][q][k][r] (item = (q,r)) ---------------------
+// LAYOUT 1: U[(i*K2 + qr)*UP + p] (reverse sweep); LAYOUT 2: U[(i*K + p)*UQ + qr] (forward sweep)
+template <int K, int LAYOUT>
 TNQ_HD void phase_b(const WarpCtx<K>& c, int lane, const float* Xn) {
     using D = Dims<K>;
     const int s = lane / D::IPS, qr = lane % D::IPS, q = qr / K, r = qr % K;
@@ -262,7 +344,12 @@ TNQ_HD void phase_b(const WarpCtx<K>& c, int lane, const float* Xn) {
             }
             u[p] = a;
         }
-        stv<D::UP>(c.U + s * D::USZ + (i * D::K2 + qr) * D::UP, u);
+        if (LAYOUT == 1) {
+            stv<D::UP>(c.U + s * D::USZ + (i * D::K2 + qr) * D::UP, u);
+        } else {
+            TNQ_UNROLL
+            for (int p = 0; p < K; ++p) c.U[s * D::USZ + (i * K + p) * D::UQ + qr] = u[p];
+        }
     }
 }
 
@@ -278,7 +365,7 @@ TNQ_HD void fill_t2_first(const WarpCtx<K>& c, int lane, const float* As0) {
         for (int p = 0; p < K; ++p) t2[g * K + p] = As0[g * K + f] * As0[p * K + o];
 }
 
-// ---- phase C: T2, U -> E' (item = (f,o)) ----------------------------------------------------
+// ---- phase C: T2, U -> E' (item = (f,o)); vectors run over (q,r) ---------------------------------
 template <int K>
 TNQ_HD void phase_c_fwd(const WarpCtx<K>& c, int lane, const float* Xt) {
     using D = Dims<K>;
@@ -288,34 +375,30 @@ TNQ_HD void phase_c_fwd(const WarpCtx<K>& c, int lane, const float* Xt) {
     for (int g = 0; g < K; ++g)
         TNQ_UNROLL
         for (int p = 0; p < K; ++p) t2[g][p] = c.T2[s * D::K4 + fo * D::K2 + g * K + p];
-    float V[D::K2][D::K2];   // [qr][g*K+i]
+    Vec<D::K2> V[D::K2];     // [g*K+i] over qr
+    TNQ_UNROLL
+    for (int gi = 0; gi < D::K2; ++gi) V[gi].zero();
     const float* U = c.U + s * D::USZ;
     TNQ_UNROLL
-    for (int qr = 0; qr < D::K2; ++qr)
+    for (int i = 0; i < K; ++i)
         TNQ_UNROLL
-        for (int i = 0; i < K; ++i) {
-            float u[D::UP];
-            ldv<D::UP>(U + (i * D::K2 + qr) * D::UP, u);
+        for (int p = 0; p < K; ++p) {
+            Vec<D::K2> u;
+            vload<D::K2>(u, U + (i * K + p) * D::UQ);
             TNQ_UNROLL
-            for (int g = 0; g < K; ++g) {
-                float a = 0.f;
-                TNQ_UNROLL
-                for (int p = 0; p < K; ++p) a = fmaf(t2[g][p], u[p], a);
-                V[qr][g * K + i] = a;
-            }
+            for (int g = 0; g < K; ++g) axpy(V[g * K + i], t2[g][p], u);
         }
     float* e = c.E + s * D::SST + fo * D::PITCH;
     TNQ_UNROLL
     for (int hj = 0; hj < D::K2; ++hj) {
         float xt[D::XTP];
         ldv<D::XTP>(Xt + hj * D::XTP, xt);
+        Vec<D::K2> out;
+        out.zero();
         TNQ_UNROLL
-        for (int qr = 0; qr < D::K2; ++qr) {
-            float a = 0.f;
-            TNQ_UNROLL
-            for (int gi = 0; gi < D::K2; ++gi) a = fmaf(V[qr][gi], xt[gi], a);
-            e[qr * D::K2 + hj] = a;
-        }
+        for (int gi = 0; gi < D::K2; ++gi) axpy(out, xt[gi], V[gi]);
+        TNQ_UNROLL
+        for (int qr = 0; qr < D::K2; ++qr) e[qr * D::K2 + hj] = out.get(qr);
     }
 }
 
@@ -390,7 +473,7 @@ TNQ_HD void last_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const floa
     float t2[K][K], P2[K][K][K];
     last_p2<K>(c, lane, Xn, t2, P2);
     TNQ_UNROLL
-    for (int v = 0; v < D::K4; ++v) st.accX[v] = 0.f;
+    for (int v = 0; v < D::K2; ++v) st.accX[v].zero();
     float dP2[K][K][K];      // [g][h][p']
     TNQ_UNROLL
     for (int g = 0; g < K; ++g)
@@ -404,8 +487,9 @@ TNQ_HD void last_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const floa
                 float cx = 0.f;   // d X[g][f][h][i]
                 TNQ_UNROLL
                 for (int pp = 0; pp < K; ++pp) cx = fmaf(st.pf[i * K + pp], P2[g][h][pp], cx);
-                TNQ_UNROLL
-                for (int F = 0; F < K; ++F) st.accX[((g * K + F) * K + h) * K + i] += (F == f) ? cx : 0.f;
+                TNQ_UNROLL           // X[g][F][h][i]: accX[g*K + h] component (F, i)
+                for (int F = 0; F < K; ++F)
+                    st.accX[g * K + h].set(F * K + i, st.accX[g * K + h].get(F * K + i) + ((F == f) ? cx : 0.f));
             }
             TNQ_UNROLL
             for (int pp = 0; pp < K; ++pp) {
@@ -449,8 +533,9 @@ TNQ_HD void last_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const floa
                     dt2[g][p0] = fmaf(dP1[g][j][pp], x, dt2[g][p0]);
                     cx = fmaf(t2[g][p0], dP1[g][j][pp], cx);
                 }
-                TNQ_UNROLL
-                for (int O = 0; O < K; ++O) st.accX[((p0 * K + O) * K + j) * K + pp] += (O == o) ? cx : 0.f;
+                TNQ_UNROLL           // X[p0][O][j][p']: accX[p0*K + j] component (O, p')
+                for (int O = 0; O < K; ++O)
+                    st.accX[p0 * K + j].set(O * K + pp, st.accX[p0 * K + j].get(O * K + pp) + ((O == o) ? cx : 0.f));
             }
     TNQ_UNROLL
     for (int g = 0; g < K; ++g)
@@ -459,66 +544,60 @@ TNQ_HD void last_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const floa
 }
 
 // ---- reverse of phase C (item = (f,o)): D holds dE' on entry and Z = dV on exit ---------------
+// per (q,r) slice:  v[g][i] = sum_p T2[g][p] U[i][p]      accX[g][i][(h,j)] += v[g][i] dE'[(h,j)]
+//                   z[(g,i)] = sum_(h,j) dE'[(h,j)] Xt[(h,j)][(g,i)]     dT2[g][p] += z[g][i] U[i][p]
 template <int K>
 TNQ_HD void phase_c_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const float* Xt) {
     using D = Dims<K>;
     const int s = lane / D::IPS, fo = lane % D::IPS;
-    float t2[K][K], dt2[K][K];
+    Vec<K> t2T[K], dt2[K];   // t2T[p] over g ; dt2[g] over p
     TNQ_UNROLL
-    for (int g = 0; g < K; ++g)
+    for (int g = 0; g < K; ++g) {
+        dt2[g].zero();
         TNQ_UNROLL
-        for (int p = 0; p < K; ++p) {
-            t2[g][p] = c.T2[s * D::K4 + fo * D::K2 + g * K + p];
-            dt2[g][p] = 0.f;
-        }
+        for (int p = 0; p < K; ++p) t2T[p].set(g, c.T2[s * D::K4 + fo * D::K2 + g * K + p]);
+    }
     TNQ_UNROLL
-    for (int v = 0; v < D::K4; ++v) st.accX[v] = 0.f;
+    for (int v = 0; v < D::K2; ++v) st.accX[v].zero();
     const float* U = c.U + s * D::USZ;
     float* d = c.D + s * D::SST + fo * D::PITCH;
     TNQ_NOUNROLL
     for (int qr = 0; qr < D::K2; ++qr) {
-        float u[K][D::UP];   // [i][p]
+        Vec<K> u[K];         // [i] over p
         TNQ_UNROLL
-        for (int i = 0; i < K; ++i) ldv<D::UP>(U + (i * D::K2 + qr) * D::UP, u[i]);
-        float de[D::K2];     // [h*K+j]
+        for (int i = 0; i < K; ++i) vload<K>(u[i], U + (i * D::K2 + qr) * D::UP);
+        Vec<D::K2> de;       // over (h,j)
         TNQ_UNROLL
-        for (int hj = 0; hj < D::K2; ++hj) de[hj] = d[qr * D::K2 + hj];
-        float z[D::K2];      // [g*K+i]
+        for (int hj = 0; hj < D::K2; ++hj) de.set(hj, d[qr * D::K2 + hj]);
         TNQ_UNROLL
-        for (int gi = 0; gi < D::K2; ++gi) z[gi] = 0.f;
-        TNQ_UNROLL
-        for (int g = 0; g < K; ++g)
+        for (int i = 0; i < K; ++i) {
+            Vec<K> v;        // over g
+            v.zero();
             TNQ_UNROLL
-            for (int i = 0; i < K; ++i) {
-                float v = 0.f;
-                TNQ_UNROLL
-                for (int p = 0; p < K; ++p) v = fmaf(t2[g][p], u[i][p], v);
-                TNQ_UNROLL
-                for (int h = 0; h < K; ++h)
-                    TNQ_UNROLL
-                    for (int j = 0; j < K; ++j)
-                        st.accX[((g * K + h) * K + i) * K + j] = fmaf(v, de[h * K + j], st.accX[((g * K + h) * K + i) * K + j]);
-            }
+            for (int p = 0; p < K; ++p) axpy(v, u[i].get(p), t2T[p]);
+            TNQ_UNROLL
+            for (int g = 0; g < K; ++g) axpy(st.accX[g * K + i], v.get(g), de);
+        }
+        Vec<D::K2> z;        // over (g,i)
+        z.zero();
         TNQ_UNROLL
         for (int hj = 0; hj < D::K2; ++hj) {
-            float xt[D::XTP];
-            ldv<D::XTP>(Xt + hj * D::XTP, xt);
-            TNQ_UNROLL
-            for (int gi = 0; gi < D::K2; ++gi) z[gi] = fmaf(de[hj], xt[gi], z[gi]);
+            Vec<D::K2> xt;
+            vload<D::K2>(xt, Xt + hj * D::XTP);
+            axpy(z, de.get(hj), xt);
         }
         TNQ_UNROLL
         for (int g = 0; g < K; ++g)
             TNQ_UNROLL
             for (int i = 0; i < K; ++i) {
-                TNQ_UNROLL
-                for (int p = 0; p < K; ++p) dt2[g][p] = fmaf(z[g * K + i], u[i][p], dt2[g][p]);
-                d[qr * D::K2 + g * K + i] = z[g * K + i];
+                axpy(dt2[g], z.get(g * K + i), u[i]);
+                d[qr * D::K2 + g * K + i] = z.get(g * K + i);
             }
     }
     TNQ_UNROLL
     for (int g = 0; g < K; ++g)
         TNQ_UNROLL
-        for (int p = 0; p < K; ++p) c.dT2[s * D::K4 + fo * D::K2 + g * K + p] = dt2[g][p];
+        for (int p = 0; p < K; ++p) c.dT2[s * D::K4 + fo * D::K2 + g * K + p] = dt2[g].get(p);
 }
 
 // dU[i][p] of this item's (q,r) from Z and T2, then the right-hand-copy contribution to dX:
@@ -527,103 +606,64 @@ template <int K>
 TNQ_HD void phase_du(const WarpCtx<K>& c, int lane) {
     using D = Dims<K>;
     const int s = lane / D::IPS, qr = lane % D::IPS, q = qr / K, r = qr % K;
-    float du[K][K];          // [i][p]
+    Vec<K> du[K];            // [i] over p
     TNQ_UNROLL
-    for (int i = 0; i < K; ++i)
-        TNQ_UNROLL
-        for (int p = 0; p < K; ++p) du[i][p] = 0.f;
+    for (int i = 0; i < K; ++i) du[i].zero();
     const float* z = c.D + s * D::SST + qr * D::K2;
     const float* t2 = c.T2 + s * D::K4;
     TNQ_UNROLL
     for (int fo = 0; fo < D::K2; ++fo)
         TNQ_UNROLL
         for (int g = 0; g < K; ++g) {
-            float zz[K], tt[K];
+            Vec<K> tt;
             TNQ_UNROLL
-            for (int i = 0; i < K; ++i) zz[i] = z[fo * D::PITCH + g * K + i];
+            for (int p = 0; p < K; ++p) tt.set(p, t2[fo * D::K2 + g * K + p]);
             TNQ_UNROLL
-            for (int p = 0; p < K; ++p) tt[p] = t2[fo * D::K2 + g * K + p];
-            TNQ_UNROLL
-            for (int i = 0; i < K; ++i)
-                TNQ_UNROLL
-                for (int p = 0; p < K; ++p) du[i][p] = fmaf(zz[i], tt[p], du[i][p]);
+            for (int i = 0; i < K; ++i) axpy(du[i], z[fo * D::PITCH + g * K + i], tt);
         }
     float* xr = c.U + s * D::USZ;
     TNQ_UNROLL
     for (int k = 0; k < K; ++k) {
-        float m[K];
+        Vec<K> w;            // over p
+        w.zero();
         TNQ_UNROLL
-        for (int i = 0; i < K; ++i) m[i] = c.M[s * D::K2 + i * K + k];
+        for (int i = 0; i < K; ++i) axpy(w, c.M[s * D::K2 + i * K + k], du[i]);
         TNQ_UNROLL
-        for (int p = 0; p < K; ++p) {
-            float a = 0.f;
-            TNQ_UNROLL
-            for (int i = 0; i < K; ++i) a = fmaf(m[i], du[i][p], a);
-            xr[((p * K + q) * K + k) * K + r] = a;
-        }
+        for (int p = 0; p < K; ++p) xr[((p * K + q) * K + k) * K + r] = w.get(p);
     }
 }
 
 // ---- reverse of phase A (item = (p,g)): E, dT2 -> dE (into D) and accB --------------------------
+//   X2[f][(l,n)] = dT1 = sum_o Bs[l][n][o] dT2[f][o]
+//   dBs[l][n][o] += T1[f][(l,n)] dT2[f][o]            dBs[c][e][f] += sum_(l,n) Epg[c][e][(l,n)] X2[f][(l,n)]
+//   dE[c][e][(l,n)] = sum_f Bs[c][e][f] X2[f][(l,n)]
 template <int K>
-TNQ_HD void phase_a_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const float* Bs) {
+TNQ_HD void phase_a_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const float* Bs, const float* BsT) {
     using D = Dims<K>;
     const int s = lane / D::IPS, it = lane % D::IPS, p = it / K, g = it % K;
-    const float* e = c.E + s * D::SST + p * D::K2 + g;
-    float Epg[K][K][K][K];   // [c][l][n][e]
-    TNQ_UNROLL
-    for (int cc = 0; cc < K; ++cc)
-        TNQ_UNROLL
-        for (int l = 0; l < K; ++l)
-            TNQ_UNROLL
-            for (int n = 0; n < K; ++n)
-                TNQ_UNROLL
-                for (int ee = 0; ee < K; ++ee) Epg[cc][l][n][ee] = e[(cc * K + l) * D::PITCH + n * D::K3 + ee * K];
-    float dt[K][K];          // [f][o]
+    Vec<D::K2> Epg[K][K], T1[K], X2[K];
+    gather_epg<K>(c.E + s * D::SST + p * D::K2 + g, Epg);
+    Vec<K> dt[K];            // [f] over o
     TNQ_UNROLL
     for (int f = 0; f < K; ++f)
         TNQ_UNROLL
-        for (int o = 0; o < K; ++o) dt[f][o] = c.dT2[s * D::K4 + (f * K + o) * D::K2 + g * K + p];
+        for (int o = 0; o < K; ++o) dt[f].set(o, c.dT2[s * D::K4 + (f * K + o) * D::K2 + g * K + p]);
+    contract_t1<K>(Bs, Epg, T1);
     TNQ_UNROLL
-    for (int v = 0; v < D::K3; ++v) st.accB[v] = 0.f;
-    float T1[K][K][K];       // [f][l][n]
-    TNQ_UNROLL
-    for (int f = 0; f < K; ++f)
+    for (int ln = 0; ln < D::K2; ++ln) {
+        st.accB[ln].zero();
         TNQ_UNROLL
-        for (int l = 0; l < K; ++l)
-            TNQ_UNROLL
-            for (int n = 0; n < K; ++n) T1[f][l][n] = 0.f;
+        for (int f = 0; f < K; ++f) axpy(st.accB[ln], T1[f].get(ln), dt[f]);
+    }
     TNQ_UNROLL
-    for (int cc = 0; cc < K; ++cc)
-        TNQ_UNROLL
-        for (int ee = 0; ee < K; ++ee) {
-            float bs[D::BSP];
-            ldv<D::BSP>(Bs + (cc * K + ee) * D::BSP, bs);
-            TNQ_UNROLL
-            for (int l = 0; l < K; ++l)
-                TNQ_UNROLL
-                for (int n = 0; n < K; ++n)
-                    TNQ_UNROLL
-                    for (int f = 0; f < K; ++f) T1[f][l][n] = fmaf(bs[f], Epg[cc][l][n][ee], T1[f][l][n]);
-        }
-    float X2[K][K][K];       // [f][l][n] = d T1
+    for (int f = 0; f < K; ++f) X2[f].zero();
     TNQ_UNROLL
-    for (int l = 0; l < K; ++l)
+    for (int o = 0; o < K; ++o) {
+        Vec<D::K2> bt;
+        vload<D::K2>(bt, BsT + o * D::BTP);
         TNQ_UNROLL
-        for (int n = 0; n < K; ++n) {
-            float bs[D::BSP];
-            ldv<D::BSP>(Bs + (l * K + n) * D::BSP, bs);
-            TNQ_UNROLL
-            for (int f = 0; f < K; ++f) {
-                float a = 0.f;
-                TNQ_UNROLL
-                for (int o = 0; o < K; ++o) {
-                    a = fmaf(bs[o], dt[f][o], a);
-                    st.accB[(l * K + n) * K + o] = fmaf(T1[f][l][n], dt[f][o], st.accB[(l * K + n) * K + o]);
-                }
-                X2[f][l][n] = a;
-            }
-        }
+        for (int f = 0; f < K; ++f) axpy(X2[f], dt[f].get(o), bt);
+    }
     float* d = c.D + s * D::SST + p * D::K2 + g;
     TNQ_UNROLL
     for (int cc = 0; cc < K; ++cc)
@@ -631,28 +671,27 @@ TNQ_HD void phase_a_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const f
         for (int ee = 0; ee < K; ++ee) {
             float bs[D::BSP];
             ldv<D::BSP>(Bs + (cc * K + ee) * D::BSP, bs);
+            Vec<D::K2> de;
+            de.zero();
+            TNQ_UNROLL
+            for (int f = 0; f < K; ++f) {
+                axpy(de, bs[f], X2[f]);
+                st.accB[cc * K + ee].set(f, dot(Epg[cc][ee], X2[f], st.accB[cc * K + ee].get(f)));
+            }
             TNQ_UNROLL
             for (int l = 0; l < K; ++l)
                 TNQ_UNROLL
-                for (int n = 0; n < K; ++n) {
-                    float a = 0.f;
-                    TNQ_UNROLL
-                    for (int f = 0; f < K; ++f) {
-                        a = fmaf(bs[f], X2[f][l][n], a);
-                        st.accB[(cc * K + ee) * K + f] = fmaf(Epg[cc][l][n][ee], X2[f][l][n], st.accB[(cc * K + ee) * K + f]);
-                    }
-                    d[(cc * K + l) * D::PITCH + n * D::K3 + ee * K] = a;
-                }
+                for (int n = 0; n < K; ++n) d[(cc * K + l) * D::PITCH + n * D::K3 + ee * K] = de.get(l * K + n);
         }
 }
 
-// first step, reverse of T2 = As0 (x) As0 (item = (f,o)): accB[0..K2) = this lane's d As0[e][f]
+// first step, reverse of T2 = As0 (x) As0 (item = (f,o)): accB[e] over f = this lane's d As0[e][f]
 template <int K>
 TNQ_HD void first_a_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const float* As0) {
     using D = Dims<K>;
     const int s = lane / D::IPS, fo = lane % D::IPS, f = fo / K, o = fo % K;
     TNQ_UNROLL
-    for (int v = 0; v < D::K3; ++v) st.accB[v] = 0.f;
+    for (int v = 0; v < K; ++v) st.accB[v].zero();
     float dt[K][K];
     TNQ_UNROLL
     for (int g = 0; g < K; ++g)
@@ -664,7 +703,7 @@ TNQ_HD void first_a_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const f
         TNQ_UNROLL
         for (int p = 0; p < K; ++p) cl = fmaf(dt[g][p], As0[p * K + o], cl);
         TNQ_UNROLL
-        for (int F = 0; F < K; ++F) st.accB[g * K + F] += (F == f) ? cl : 0.f;
+        for (int F = 0; F < K; ++F) st.accB[g].set(F, st.accB[g].get(F) + ((F == f) ? cl : 0.f));
     }
     TNQ_UNROLL
     for (int p = 0; p < K; ++p) {
@@ -672,7 +711,7 @@ TNQ_HD void first_a_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const f
         TNQ_UNROLL
         for (int g = 0; g < K; ++g) cr = fmaf(dt[g][p], As0[g * K + f], cr);
         TNQ_UNROLL
-        for (int O = 0; O < K; ++O) st.accB[p * K + O] += (O == o) ? cr : 0.f;
+        for (int O = 0; O < K; ++O) st.accB[p].set(O, st.accB[p].get(O) + ((O == o) ? cr : 0.f));
     }
 }
 
@@ -687,11 +726,25 @@ TNQ_HD void gadd(float* p, float v) {
 }
 
 // ---- lane reduction: scratch[v][lane] then row sums in lane order -> += gp[v] ---------------------
-template <int K, int NV>
-TNQ_HD void flush_put(float* scr, int lane, const float* acc) {
+template <int K>
+TNQ_HD void flush_put_x(float* scr, int lane, const Vec<Dims<K>::K2> (&acc)[Dims<K>::K2]) {
     using D = Dims<K>;
     TNQ_UNROLL
-    for (int v = 0; v < NV; ++v) scr[v * D::LP + lane] = acc[v];
+    for (int g = 0; g < K; ++g)
+        TNQ_UNROLL
+        for (int h = 0; h < K; ++h)
+            TNQ_UNROLL
+            for (int i = 0; i < K; ++i)
+                TNQ_UNROLL
+                for (int j = 0; j < K; ++j) scr[(((g * K + h) * K + i) * K + j) * D::LP + lane] = acc[g * K + i].get(h * K + j);
+}
+template <int K, int NROWS>
+TNQ_HD void flush_put_b(float* scr, int lane, const Vec<K> (&acc)[Dims<K>::K2]) {
+    using D = Dims<K>;
+    TNQ_UNROLL
+    for (int ab = 0; ab < NROWS; ++ab)
+        TNQ_UNROLL
+        for (int cc = 0; cc < K; ++cc) scr[(ab * K + cc) * D::LP + lane] = acc[ab].get(cc);
 }
 template <int K, int NV, bool WITH_XR>
 TNQ_HD void flush_sum(const float* scr, const float* xr, int lane, float* gp) {
@@ -790,6 +843,7 @@ TNQ_HD void ladder_group(const WarpCtx<K>& c, TNQ_LANES_PARAM, long long b0) {
 #define TNQ_XN(q) (c.cst + (q) * D::CSTEP + D::OFF_XN)
 #define TNQ_XT(q) (c.cst + (q) * D::CSTEP + D::OFF_XT)
 #define TNQ_BS(q) (c.cst + (q) * D::CSTEP + D::OFF_BS)
+#define TNQ_BT(q) (c.cst + (q) * D::CSTEP + D::OFF_BT)
 #define TNQ_GX(q) (c.gpart + (q) * D::K4)
 #define TNQ_GB(q) (c.gpart + (n - 1) * D::K4 + (q) * D::K3)
 #define TNQ_GA0 (c.gpart + (n - 1) * D::K4 + (n - 1) * D::K3)
@@ -800,7 +854,7 @@ TNQ_HD void ladder_group(const WarpCtx<K>& c, TNQ_LANES_PARAM, long long b0) {
         st.mnext = load_m<K>(c, 1, b0 + TNQ_S, TNQ_IT);
         fill_t2_first<K>(c, lane, As0);
     })
-    TNQ_PHASE(if (TNQ_ACTIVE) phase_b<K>(c, lane, TNQ_XN(0));)
+    TNQ_PHASE(if (TNQ_ACTIVE) phase_b<K, 2>(c, lane, TNQ_XN(0));)
     TNQ_PHASE(if (TNQ_ACTIVE) phase_c_fwd<K>(c, lane, TNQ_XT(0));)
     for (int q = 1; q <= n - 2; ++q) {
         TNQ_PHASE(
@@ -813,7 +867,7 @@ TNQ_HD void ladder_group(const WarpCtx<K>& c, TNQ_LANES_PARAM, long long b0) {
         if (q < n - 2) {
             TNQ_PHASE(
                 if (CK) ckpt_store<D::T2_SZ>(c.ckT2 + (size_t)(q - 1) * D::T2_SZ, c.T2, lane);
-                if (TNQ_ACTIVE) phase_b<K>(c, lane, TNQ_XN(q));)
+                if (TNQ_ACTIVE) phase_b<K, 2>(c, lane, TNQ_XN(q));)
             TNQ_PHASE(if (TNQ_ACTIVE) phase_c_fwd<K>(c, lane, TNQ_XT(q));)
         }
     }
@@ -862,7 +916,7 @@ TNQ_HD void ladder_group(const WarpCtx<K>& c, TNQ_LANES_PARAM, long long b0) {
     })
     TNQ_PHASE(if (TNQ_ACTIVE) {
         last_bwd<K>(c, st, lane, TNQ_XN(n - 2));
-        flush_put<K, D::K4>(c.D, lane, st.accX);
+        flush_put_x<K>(c.D, lane, st.accX);
     })
     // cp.async groups are committed alternately: T2 of the next step (after this step's last use of
     // the T2 buffer), then E of that step (at its start); every wait leaves the newest group pending
@@ -880,20 +934,20 @@ TNQ_HD void ladder_group(const WarpCtx<K>& c, TNQ_LANES_PARAM, long long b0) {
                     st.mnext = load_m<K>(c, q - 1, b0 + TNQ_S, TNQ_IT);
                 })
             TNQ_PHASE(
-                if (TNQ_ACTIVE) phase_b<K>(c, lane, TNQ_XN(q));
+                if (TNQ_ACTIVE) phase_b<K, 1>(c, lane, TNQ_XN(q));
                 ckpt_wait<1>();)                                  // T2_q has landed
             TNQ_PHASE(if (TNQ_ACTIVE) phase_c_bwd<K>(c, st, lane, TNQ_XT(q));)
             TNQ_PHASE(if (TNQ_ACTIVE) phase_du<K>(c, lane);)
             TNQ_PHASE(
-                if (TNQ_ACTIVE) flush_put<K, D::K4>(c.D, lane, st.accX);
+                if (TNQ_ACTIVE) flush_put_x<K>(c.D, lane, st.accX);
                 if (q - 1 >= 1) ckpt_load_async<D::T2_SZ>(c.T2, c.ckT2 + (size_t)(q - 2) * D::T2_SZ, lane);
                 ckpt_commit();)
             TNQ_PHASE(
                 flush_sum<K, D::K4, true>(c.D, c.U, lane, TNQ_GX(q));
                 ckpt_wait<1>();)                                  // E_q has landed
         }
-        TNQ_PHASE(if (TNQ_ACTIVE) phase_a_bwd<K>(c, st, lane, TNQ_BS(q));)
-        TNQ_PHASE(if (TNQ_ACTIVE) flush_put<K, D::K3>(c.E, lane, st.accB);)
+        TNQ_PHASE(if (TNQ_ACTIVE) phase_a_bwd<K>(c, st, lane, TNQ_BS(q), TNQ_BT(q));)
+        TNQ_PHASE(if (TNQ_ACTIVE) flush_put_b<K, D::K2>(c.E, lane, st.accB);)
         TNQ_PHASE(flush_sum<K, D::K3, false>(c.E, nullptr, lane, TNQ_GB(q));)
     }
     TNQ_PHASE(ckpt_wait<0>();)
@@ -902,14 +956,14 @@ TNQ_HD void ladder_group(const WarpCtx<K>& c, TNQ_LANES_PARAM, long long b0) {
         c.M[lane] = st.mnext;
         fill_t2_first<K>(c, lane, As0);
     })
-    TNQ_PHASE(if (TNQ_ACTIVE) phase_b<K>(c, lane, TNQ_XN(0));)
+    TNQ_PHASE(if (TNQ_ACTIVE) phase_b<K, 1>(c, lane, TNQ_XN(0));)
     TNQ_PHASE(if (TNQ_ACTIVE) phase_c_bwd<K>(c, st, lane, TNQ_XT(0));)
     TNQ_PHASE(if (TNQ_ACTIVE) phase_du<K>(c, lane);)
-    TNQ_PHASE(if (TNQ_ACTIVE) flush_put<K, D::K4>(c.D, lane, st.accX);)
+    TNQ_PHASE(if (TNQ_ACTIVE) flush_put_x<K>(c.D, lane, st.accX);)
     TNQ_PHASE(flush_sum<K, D::K4, true>(c.D, c.U, lane, TNQ_GX(0));)
     TNQ_PHASE(if (TNQ_ACTIVE) {
         first_a_bwd<K>(c, st, lane, As0);
-        flush_put<K, D::K2>(c.E, lane, st.accB);
+        flush_put_b<K, K>(c.E, lane, st.accB);
     })
     TNQ_PHASE(flush_sum<K, D::K2, false>(c.E, nullptr, lane, TNQ_GA0);)
 #undef TNQ_ACTIVE
@@ -918,6 +972,7 @@ TNQ_HD void ladder_group(const WarpCtx<K>& c, TNQ_LANES_PARAM, long long b0) {
 #undef TNQ_XN
 #undef TNQ_XT
 #undef TNQ_BS
+#undef TNQ_BT
 #undef TNQ_GX
 #undef TNQ_GB
 #undef TNQ_GA0
@@ -943,10 +998,18 @@ TNQ_HD float const_pool_element(const Args& a, int idx) {
         const int h = hj / K, j = hj % K, g = gi / K, i = gi % K;
         return a.coreX[q][((g * K + h) * K + i) * K + j];
     }
-    const int t = r - D::OFF_BS;
-    if (t >= D::K2 * D::BSP || q == 0) return 0.f;
-    const int ce = t / D::BSP, f = t % D::BSP;    // Bs[c][e][f] = sum_d A_q[c][d][e][f] s_{q+1}[d]
-    if (f >= K) return 0.f;
+    if (q == 0) return 0.f;
+    int ce, f;                                  // Bs[c][e][f] = sum_d A_q[c][d][e][f] s_{q+1}[d]
+    if (r < D::OFF_BT) {
+        const int t = r - D::OFF_BS;
+        if (t >= D::K2 * D::BSP) return 0.f;
+        ce = t / D::BSP, f = t % D::BSP;
+    } else {                                    // transposed copy BsT[f][(c,e)]
+        const int t = r - D::OFF_BT;
+        if (t >= K * D::BTP) return 0.f;
+        f = t / D::BTP, ce = t % D::BTP;
+    }
+    if (f >= K || ce >= D::K2) return 0.f;
     const int cc = ce / K, e = ce % K;
     float v = 0.f;
     for (int d = 0; d < K; ++d) v = fmaf(a.coreA[q][((cc * K + d) * K + e) * K + f], a.state[q + 1][d], v);
