@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="do not replay the training step from a CUDA graph")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -261,6 +262,7 @@ def main():
 
     backend = tb.BackendFactory.create_backend("b200", device=str(dev), dtype=wl["dtype"])
     engine = tb.EngineSiamese(backend=backend, strategy_mode="balanced", mx_K=K)
+    engine.enable_cuda_graphs(not args.no_graphs)      # opt-in product feature (EngineSiamese.enable_cuda_graphs)
     qctn = tb.QCTN(graph, backend=backend)
     for c in names:
         w = cores_cpu[c].to(dev).clone(memory_format=torch.contiguous_format)
@@ -305,8 +307,18 @@ def main():
         with torch.no_grad():
             return fn(cores_dict, states, mx_dev).tensor
 
+    use_graphs = train and not args.no_graphs
+    mx_static = [torch.empty_like(m.tensor) for m in mx_dev] if use_graphs else None
+
     def step_e2e():
-        mxs = [tb.TNTensor(h.to(dev, non_blocking=True), sc, ls) for h, (sc, ls) in zip(mx_host, mx_scales)]
+        if use_graphs:
+            # CUDA-graph contract (EngineSiamese.enable_cuda_graphs): the batch is copied from pinned
+            # host memory into STATIC device buffers, so the captured step can be replayed
+            for d, h in zip(mx_static, mx_host):
+                d.copy_(h, non_blocking=True)
+            mxs = [tb.TNTensor(d, sc, ls) for d, (sc, ls) in zip(mx_static, mx_scales)]
+        else:
+            mxs = [tb.TNTensor(h.to(dev, non_blocking=True), sc, ls) for h, (sc, ls) in zip(mx_host, mx_scales)]
         if train:
             loss, grads = engine.contract_with_compiled_strategy_for_gradient(qctn, states, mxs)
             if dist is not None:
@@ -444,6 +456,7 @@ def main():
             "dtype": "f32" if esz == 4 else "c64 (real fp32 arithmetic: 3xTF32 on tcgen05)", "data": "synthetic",
             "config": {"workload": wl["name"], "global_batch": B_global, "per_gpu_batch": B, "qubits": nq, "K": K,
                        "cores": len(names), "l2": "flushed between timed steps (256 MiB write)",
+                       "cuda_graphs": bool(train and not args.no_graphs),
                        "parallelism": f"batch sharded over {world} GPU(s); cores replicated; "
                                       + ("one packed NCCL all-reduce of grads+loss per step" if world > 1 else "no collective")},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}

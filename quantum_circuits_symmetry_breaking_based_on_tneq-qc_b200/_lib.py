@@ -75,5 +75,16 @@ def check(rc: int):
         raise RuntimeError("tneq_b200: " + load().tnq_last_error().decode("utf-8", "replace"))
 
 
+_graph_launches = 0
+
+
+def add_graph_launches(n: int) -> None:
+    """Kernels of this library that ran through a CUDA-graph replay (they are launched by
+    cudaGraphLaunch, not by the library's own launch sites)."""
+    global _graph_launches
+    _graph_launches += int(n)
+
+
 def launch_count() -> int:
-    return int(load().tnq_launch_count())
+    """Kernels of this library launched so far, directly or by graph replay."""
+    return int(load().tnq_launch_count()) + _graph_launches

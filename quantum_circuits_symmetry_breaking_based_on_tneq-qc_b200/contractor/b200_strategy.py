@@ -22,10 +22,12 @@ forward + loss + reverse sweep as one fused device program.
 from __future__ import annotations
 
 import math
+import os
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import torch
 
+from .. import _lib as _lib_mod
 from ..core.tn_tensor import TNTensor
 from .base import ContractionStrategy
 from .device_plan import DeviceProgram
@@ -35,8 +37,18 @@ _DTYPE_NAME = {torch.float32: "float32", torch.float64: "float64",
                torch.complex64: "complex64", torch.complex128: "complex128"}
 
 
+# process-wide switch for CUDA-graph replay of the fused training step (see loss_and_grads below);
+# also set by the environment variable TNQ_CUDA_GRAPHS=1
+_GRAPHS = {"enabled": False}
+
+
+def set_cuda_graphs(flag: bool = True) -> None:
+    _GRAPHS["enabled"] = bool(flag)
+
+
 def _is_tnt(x) -> bool:
-    return hasattr(x, "tensor") and hasattr(x, "scale") and hasattr(x, "log_scale")
+    # duck-typed: the reference's own TNTensor class is accepted too (reference_plugin.py)
+    return (not isinstance(x, torch.Tensor)) and hasattr(x, "tensor") and hasattr(x, "scale") and hasattr(x, "log_scale")
 
 
 def _raw(x):
@@ -73,13 +85,29 @@ class _Bound:
         self.use_gemm_path = biggest > VM_MAX_CORE_ELEMS or os.environ.get("TNQ_FORCE_GEMM_PATH") == "1"
         self.chain_rank = 0 if (self.use_gemm_path or os.environ.get("TNQ_NO_CHAIN") == "1") else plan.mps_chain_rank()
         self._chain_ws = None
+        self._scale_prog = None
         # two-layer merged MPS: warp-level ladder kernel (csrc/tnq_ladder.cu)
-        self.ladder = None
+        self.ladder, self._ladder_order, self._ladder_ws_bytes = None, None, {}
         if not (self.use_gemm_path or self.chain_rank or os.environ.get("TNQ_NO_CHAIN") == "1"):
             self.ladder = plan.mps_ladder()
         if self.use_gemm_path and plan.real_dtype != "f32":
             raise NotImplementedError("large-bond contraction runs on the tensor cores in float32 / complex64 only; "
                                       f"got {plan.dtype} with a core of {biggest} elements")
+
+    def scale_program(self):
+        """[(tmp id produced, [(is_tmp, operand key)])] per greedy step, operands in einsum order."""
+        if self._scale_prog is None:
+            prog = []
+            for step in self.plan.schedule.steps:
+                ops = []
+                for op in step.operands:
+                    if op.kind == "tmp":
+                        ops.append((True, op.key))
+                    else:
+                        ops.append((False, ("core", op.key) if op.kind == "core_conj" else (op.kind, op.key)))
+                prog.append((step.out, ops))
+            self._scale_prog = prog
+        return self._scale_prog
 
     def gemm_runner(self, mode: str):
         from .gemm_path import GemmPathRunner
@@ -195,45 +223,66 @@ class _Call:
         return values, (loss[0] if loss is not None else None), [gmap[k] for k in self.core_keys] if grads else []
 
     # ---- two-layer merged MPS route: warp-level ladder kernel (csrc/tnq_ladder.cu) -------------
-    def _ladder(self, cores, mode, seed=None, log_scale=0.0):
+    def _ladder(self, cores, mode, seed=None, log_scale=0.0, private_ws=False):
         from ctypes import c_void_p, c_int64
         from .. import _lib
         lib = _lib.load()
-        K, layer1, layer2 = self.bound.ladder
-        n, dev = self.bound.plan.nqubits, self.bound.device
-        by_key = dict(zip(self.core_keys, cores))
-        ca = [by_key[("core", k)] for k in layer1]
-        cx = [by_key[("core", k)] for k in layer2]
-        ca = [c if c.is_contiguous() else c.contiguous() for c in ca]
-        cx = [c if c.is_contiguous() else c.contiguous() for c in cx]
-        sts = [t if t.is_contiguous() else t.contiguous() for t in (self.states[q] for q in range(n))]
+        bound = self.bound
+        K, layer1, layer2 = bound.ladder
+        n, dev, B = bound.plan.nqubits, bound.device, self.B
+        order = bound._ladder_order
+        if order is None or order[0] != self.core_keys:
+            pos = {k: i for i, k in enumerate(self.core_keys)}
+            order = bound._ladder_order = (list(self.core_keys), [pos[("core", k)] for k in layer1],
+                                           [pos[("core", k)] for k in layer2])
+        _, ia, ix = order
+        cores = [c if c.is_contiguous() else c.contiguous() for c in cores]
+        sts = [self.states[q] for q in range(n)]
+        sts = [t if t.is_contiguous() else t.contiguous() for t in sts]
         ms, strides = [], []
         for q in range(n):
             m = self.mxs[q]
             st = m.stride()
-            if st[-1] != 1 or st[-2] != K:
+            if st[2] != 1 or st[1] != K:
                 m = m.contiguous()
                 st = m.stride()
             ms.append(m)
-            strides.append(0 if (m.shape[0] == 1 and self.B != 1) else st[0])
-        ws_bytes = int(lib.tnq_mps_ladder_workspace_bytes(K, n, self.B, mode))
-        if self.bound._chain_ws is None or self.bound._chain_ws.numel() < ws_bytes:
-            self.bound._chain_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        values = torch.empty(self.B, dtype=torch.float32, device=dev) if mode != 2 else None
+            strides.append(0 if (m.shape[0] == 1 and B != 1) else st[0])
+        key = (B, mode)
+        ws_bytes = bound._ladder_ws_bytes.get(key)
+        if ws_bytes is None:
+            ws_bytes = bound._ladder_ws_bytes[key] = int(lib.tnq_mps_ladder_workspace_bytes(K, n, B, mode))
+        if private_ws:                  # captured into a CUDA graph: the graph owns its scratch
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        else:
+            if bound._chain_ws is None or bound._chain_ws.numel() < ws_bytes:
+                bound._chain_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            ws = bound._chain_ws
+        values = torch.empty(B, dtype=torch.float32, device=dev) if mode != 2 else None
         loss = torch.empty(1, dtype=torch.float32, device=dev) if mode == 1 else None
-        ga = [torch.empty_like(c) for c in ca] if mode != 0 else []
-        gx = [torch.empty_like(c) for c in cx] if mode != 0 else []
-        arr = lambda ts: (c_void_p * max(1, len(ts)))(*[t.data_ptr() for t in ts])
+        ptr = [c.data_ptr() for c in cores]
+        nc, K4 = len(cores), K ** 4
+        if mode != 0:
+            # one allocation for all core gradients, handed out as views in the caller's core order
+            flat = torch.empty(nc * K4, dtype=torch.float32, device=dev)
+            g0 = flat.data_ptr()
+            ga = (c_void_p * (n - 1))(*[g0 + 4 * K4 * i for i in ia])
+            gx = (c_void_p * (n - 1))(*[g0 + 4 * K4 * i for i in ix])
+        else:
+            flat = ga = gx = None
+        ca = (c_void_p * (n - 1))(*[ptr[i] for i in ia])
+        cx = (c_void_p * (n - 1))(*[ptr[i] for i in ix])
         with torch.cuda.device(dev):
-            _lib.check(lib.tnq_mps_ladder(K, n, arr(ca), arr(cx), arr(sts), arr(ms), (c_int64 * n)(*strides), self.B, mode,
-                                          c_void_p(seed.data_ptr()) if seed is not None else None,
-                                          c_void_p(values.data_ptr()) if values is not None else None,
-                                          c_void_p(loss.data_ptr()) if loss is not None else None,
-                                          arr(ga) if ga else None, arr(gx) if gx else None, float(log_scale),
-                                          c_void_p(self.bound._chain_ws.data_ptr()), self.bound._chain_ws.numel(),
-                                          c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
-        gmap = {("core", k): g for k, g in zip(layer1 + layer2, ga + gx)}
-        return values, (loss[0] if loss is not None else None), [gmap[k] for k in self.core_keys] if ga else []
+            _lib.check(lib.tnq_mps_ladder(K, n, ca, cx, (c_void_p * n)(*[t.data_ptr() for t in sts]),
+                                          (c_void_p * n)(*[t.data_ptr() for t in ms]), (c_int64 * n)(*strides), B, mode,
+                                          seed.data_ptr() if seed is not None else None,
+                                          values.data_ptr() if values is not None else None,
+                                          loss.data_ptr() if loss is not None else None, ga, gx, float(log_scale),
+                                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        grads = list(flat.view(nc, K, K, K, K).unbind(0)) if flat is not None else []
+        if private_ws:
+            self._keep = ws
+        return values, (loss[0] if loss is not None else None), grads
 
     # ---- large-bond route: node-by-node on the tcgen05 GEMM path ------------------------------
     def _gemm_inputs(self, cores):
@@ -300,13 +349,17 @@ class _Call:
                 grads.append(gflat.reshape(c.shape))
         return grads
 
-    def train(self, cores, log_scale: float):
+    def graphable(self) -> bool:
+        """Routes whose training step is a fixed pair of launches on caller-owned pointers."""
+        return bool(self.bound.ladder)
+
+    def train(self, cores, log_scale: float, private_ws: bool = False):
         """Fused forward + loss + reverse sweep.  Returns (loss, grads, values)."""
         if self.bound.chain_rank:
             values, loss, grads = self._chain(cores, 1, log_scale=log_scale)
             return loss, grads, values
         if self.bound.ladder:
-            values, loss, grads = self._ladder(cores, 1, log_scale=log_scale)
+            values, loss, grads = self._ladder(cores, 1, log_scale=log_scale, private_ws=private_ws)
             return loss, grads, values
         if self.bound.use_gemm_path:
             # forward nodes, then the loss seed from the forward result (element-wise, torch), then the
@@ -363,78 +416,93 @@ class B200Strategy(ContractionStrategy):
         else:
             raise ValueError("Invalid right_qctn parameter.")
 
+        core_keys = [("core", k) for k in core_names] + [("rcore", k) for k in right_names]
+
         def prepare(cores_dict, circuit_states, measure_matrices, right_cores_dict):
-            """-> (call, raw core tensors, per-operand scale bookkeeping)"""
-            cores_w = {k: cores_dict[k] for k in core_names}
-            rcores_w = {k: right_cores_dict[k] for k in right_names} if right_mode == "qctn" else {}
-            states_w, mxs_w = _items(circuit_states, nq), _items(measure_matrices, nq)
-            mxs_w = {q: m for q, m in mxs_w.items() if m is not None}
-            tensors = [_raw(v) for v in list(cores_w.values()) + list(rcores_w.values())]
-            if not tensors:
+            """-> (call, raw core tensors, per-operand scale bookkeeping).  This runs on every call:
+            one pass over the operands, everything else is cached per operand signature."""
+            T = torch.Tensor
+            tnt: Dict[Any, Any] = {}              # operands that arrived as TNTensors
+            cores = []
+            for k in core_names:
+                v = cores_dict[k]
+                if not isinstance(v, T):
+                    if _is_tnt(v):
+                        tnt[("core", k)] = v
+                        v = v.tensor
+                cores.append(v)
+            if right_mode == "qctn":
+                for k in right_names:
+                    v = right_cores_dict[k]
+                    if not isinstance(v, T):
+                        if _is_tnt(v):
+                            tnt[("rcore", k)] = v
+                            v = v.tensor
+                    cores.append(v)
+            if not cores:
                 raise RuntimeError("No tensor left after contraction")
-            dtype = tensors[0].dtype
-            for t in [_raw(v) for v in list(states_w.values()) + list(mxs_w.values())] + tensors[1:]:
-                dtype = torch.promote_types(dtype, t.dtype)
+            states_w, mxs_w = _items(circuit_states, nq), _items(measure_matrices, nq)
+            states, mxs = {}, {}
+            for q, v in states_w.items():
+                if not isinstance(v, T):
+                    if _is_tnt(v):
+                        tnt[("state", q)] = v
+                        v = v.tensor
+                states[q] = v
+            for q, v in mxs_w.items():
+                if v is None:
+                    continue
+                if not isinstance(v, T):
+                    if _is_tnt(v):
+                        tnt[("mx", q)] = v
+                        v = v.tensor
+                mxs[q] = v
+            dtypes = {t.dtype for t in cores}
+            dtypes.update(t.dtype for t in states.values())
+            dtypes.update(t.dtype for t in mxs.values())
+            dtype = cores[0].dtype
+            if len(dtypes) > 1:
+                for t in list(states.values()) + list(mxs.values()) + cores[1:]:
+                    dtype = torch.promote_types(dtype, t.dtype)
             if dtype not in _DTYPE_NAME:
                 raise ValueError(f"unsupported dtype {dtype}")
-            device = tensors[0].device
+            device = cores[0].device
             if device.type != "cuda":
                 raise RuntimeError("B200Strategy needs CUDA tensors: tneq_b200 has no CPU fallback")
-
-            def conv(t):
-                t = _raw(t)
-                if t.device != device or t.dtype != dtype:
-                    t = t.to(device=device, dtype=dtype)
-                return t
-
-            states = {q: conv(s) for q, s in states_w.items()}
-            mxs = {q: conv(m) for q, m in mxs_w.items()}
-            for q, s in states.items():
-                if s.dim() != 1:
-                    raise ValueError(f"circuit state of qubit {q} must be 1-D (got shape {tuple(s.shape)}); "
+            if len(dtypes) > 1 or any(t.device != device for t in cores) or \
+                    any(t.device != device for t in states.values()) or any(t.device != device for t in mxs.values()):
+                conv = lambda t: t if (t.device == device and t.dtype == dtype) else t.to(device=device, dtype=dtype)
+                cores = [conv(t) for t in cores]
+                states = {q: conv(t) for q, t in states.items()}
+                mxs = {q: conv(t) for q, t in mxs.items()}
+            for q, s_ in states.items():
+                if s_.dim() != 1:
+                    raise ValueError(f"circuit state of qubit {q} must be 1-D (got shape {tuple(s_.shape)}); "
                                      "batched circuit states are not supported by the greedy contraction")
             B = None
+            mx_sig = []
             for q, m in mxs.items():
-                if m.dim() not in (3, 4) or (m.dim() == 4 and m.shape[1] != 2):
-                    raise ValueError(f"measurement of qubit {q} must be (B,K,K) or (B,2,K,K), got {tuple(m.shape)}")
-                if m.shape[0] != 1:
-                    if B is not None and B != m.shape[0]:
+                nd, shp = m.dim(), m.shape
+                if nd not in (3, 4) or (nd == 4 and shp[1] != 2):
+                    raise ValueError(f"measurement of qubit {q} must be (B,K,K) or (B,2,K,K), got {tuple(shp)}")
+                if shp[0] != 1:
+                    if B is not None and B != shp[0]:
                         raise ValueError("measurement matrices disagree on the batch size")
-                    B = m.shape[0]
+                    B = shp[0]
+                mx_sig.append((q, nd, shp[-2], shp[-1]))
             if B is None:
                 B = 1
-            state_dims, mx_info = signature_of(nq, states_w, {q: mxs_w.get(q) for q in range(nq)})
-            key = (tuple(sorted(state_dims.items())), tuple(sorted(mx_info.items())), dtype, str(device))
-            if key not in plans:
-                shapes = {k: tuple(_raw(v).shape) for k, v in cores_w.items()}
-                rshapes = {k: tuple(_raw(v).shape) for k, v in rcores_w.items()}
+            key = (tuple((q, t.shape[0]) for q, t in states.items()), tuple(mx_sig), dtype, device)
+            bound = plans.get(key)
+            if bound is None:
+                state_dims, mx_info = signature_of(nq, states_w, {q: mxs_w.get(q) for q in range(nq)})
+                shapes = {k: tuple(t.shape) for k, t in zip(core_names, cores)}
+                rshapes = {k: tuple(t.shape) for k, t in zip(right_names, cores[len(core_names):])}
                 plan = ContractionPlan(table, nq, shapes, state_dims, mx_info, _DTYPE_NAME[dtype], right=right_mode,
                                        right_table=right_table, right_core_shapes=rshapes)
-                plans[key] = _Bound(plan, device)
-            bound = plans[key]
-            core_keys = [("core", k) for k in core_names] + [("rcore", k) for k in right_names]
-            cores = [conv(v) for v in list(cores_w.values()) + list(rcores_w.values())]
+                bound = plans[key] = _Bound(plan, device)
             call = _Call(bound, core_keys, states, mxs, B, dtype)
-            # TNTensor scale of the result, combined in the reference's order
-            # (greedy_strategy.py:913-933): per step, left to right over its operands
-            wrapped = {("core", k): v for k, v in cores_w.items()}
-            wrapped.update({("rcore", k): v for k, v in rcores_w.items()})
-            wrapped.update({("state", q): v for q, v in states_w.items()})
-            wrapped.update({("mx", q): v for q, v in mxs_w.items()})
-            tmp: Dict[int, Optional[Tuple[float, float]]] = {}
-            for step in bound.plan.schedule.steps:
-                sc = ls = None
-                for op in step.operands:
-                    if op.kind == "tmp":
-                        pair = tmp[op.key]
-                    else:
-                        w = wrapped[("core", op.key) if op.kind == "core_conj" else (op.kind, op.key)]
-                        pair = (w.scale, w.log_scale) if _is_tnt(w) else None
-                    if pair is not None:
-                        sc = pair[0] if sc is None else sc * pair[0]
-                        ls = pair[1] if ls is None else ls + pair[1]
-                tmp[step.out] = None if sc is None else (sc, ls)
-            return call, cores, tmp[bound.plan.schedule.result.key]
+            return call, cores, _scale_of(bound, tnt)
 
         def compute_fn(cores_dict, circuit_states, measure_matrices, right_cores_dict=None):
             call, cores, scale = prepare(cores_dict, circuit_states, measure_matrices, right_cores_dict)
@@ -446,12 +514,112 @@ class B200Strategy(ContractionStrategy):
                 return TNTensor(res, scale=scale[0], log_scale=scale[1])
             return res
 
+        # ---- CUDA-graph replay of the fused training step (opt-in) ---------------------------------
+        # A training loop calls loss_and_grads with the SAME device buffers step after step (cores are
+        # updated in place, batches are copied into static input buffers).  With graphs enabled, the
+        # second call that presents the same pointers captures the step's launches into a CUDA graph
+        # and later calls replay it: one cudaGraphLaunch instead of ~0.5 ms of per-call Python.
+        # Contract: the returned loss / gradient / value tensors of a replayed step are the graph's
+        # own output buffers -- they are overwritten by the next replay with the same operands.
+        # Capturing costs milliseconds, so it is rationed: a key must have been seen before, and a
+        # compute function captures at most `max_captures` graphs in its life (callers that allocate
+        # fresh input tensors every step present ever-changing pointers and simply stay on the direct
+        # path).
+        graphs = {"enabled": os.environ.get("TNQ_CUDA_GRAPHS") == "1", "seen": {}, "entries": {}, "max": 4,
+                  "replays": 0, "captures": 0, "max_captures": 8}
+
+        def _raw_ptrs(cores_dict, circuit_states, measure_matrices):
+            T = torch.Tensor
+            ptrs, tnts = [], []
+            for k in core_names:
+                v = cores_dict[k]
+                if not isinstance(v, T):
+                    tnts.append((("core", k), v))
+                    v = v.tensor
+                ptrs.append(v.data_ptr())
+            for q, v in _items(circuit_states, nq).items():
+                if not isinstance(v, T):
+                    tnts.append((("state", q), v))
+                    v = v.tensor
+                ptrs.append(v.data_ptr())
+            for q, v in _items(measure_matrices, nq).items():
+                if v is None:
+                    ptrs.append(0)
+                    continue
+                if not isinstance(v, T):
+                    tnts.append((("mx", q), v))
+                    v = v.tensor
+                ptrs.append(v.data_ptr())
+                ptrs.append(v.shape[0])
+            return tuple(ptrs), tnts
+
+        def _scale_of(bound, tnt):
+            if not tnt:
+                return None
+            tmp = {}
+            for out, ops in bound.scale_program():
+                sc = ls = None
+                for is_tmp, okey in ops:
+                    if is_tmp:
+                        pair = tmp[okey]
+                        if pair is None:
+                            continue
+                        s0, l0 = pair
+                    else:
+                        w = tnt.get(okey)
+                        if w is None:
+                            continue
+                        s0, l0 = w.scale, w.log_scale
+                    sc = s0 if sc is None else sc * s0
+                    ls = l0 if ls is None else ls + l0
+                tmp[out] = None if sc is None else (sc, ls)
+            return tmp[bound.plan.schedule.result.key]
+
         def loss_and_grads(cores_dict, circuit_states, measure_matrices, right_cores_dict=None):
             """Fused -mean(log(clamp(value,1e-10)) + log_scale) and its core gradients
             (engine_siamese.py:441-554), one device program."""
+            if (graphs["enabled"] or _GRAPHS["enabled"]) and right_mode != "qctn":
+                key, tnts = _raw_ptrs(cores_dict, circuit_states, measure_matrices)
+                ent = graphs["entries"].get(key)
+                if ent is not None:
+                    bound, graph, loss0, grads, values, _call, nk = ent
+                    scale = _scale_of(bound, dict(tnts))
+                    graph.replay()
+                    graphs["replays"] += 1
+                    _lib_mod.add_graph_launches(nk)
+                    # the captured kernel runs with log_scale = 0: the loss is affine in it
+                    loss = loss0 - float(scale[1]) if scale is not None else loss0
+                    return loss, grads, values, scale
+                if graphs["seen"].get(key) and graphs["captures"] < graphs["max_captures"]:
+                    call, cores, scale = prepare(cores_dict, circuit_states, measure_matrices, right_cores_dict)
+                    if call.graphable() and all(not c.requires_grad or c.is_leaf for c in cores):
+                        dev = cores[0].device
+                        torch.cuda.synchronize(dev)
+                        graph = torch.cuda.CUDAGraph()
+                        n0 = _lib_mod.launch_count()
+                        with torch.cuda.graph(graph):
+                            loss0, grads, values = call.train(cores, 0.0, private_ws=True)
+                        nk = _lib_mod.launch_count() - n0      # kernels recorded into the graph
+                        graphs["captures"] += 1
+                        graph.replay()
+                        if len(graphs["entries"]) >= graphs["max"]:
+                            graphs["entries"].pop(next(iter(graphs["entries"])))
+                        graphs["entries"][key] = (call.bound, graph, loss0, grads, values, call, nk)
+                        loss = loss0 - float(scale[1]) if scale is not None else loss0
+                        return loss, grads, values, scale
+                else:
+                    if len(graphs["seen"]) > 64:
+                        graphs["seen"].clear()
+                    graphs["seen"][key] = True
             call, cores, scale = prepare(cores_dict, circuit_states, measure_matrices, right_cores_dict)
             loss, grads, values = call.train(cores, 0.0 if scale is None else float(scale[1]))
             return loss, grads, values, scale
+
+        def enable_cuda_graphs(flag: bool = True):
+            graphs["enabled"] = bool(flag)
+            if not flag:
+                graphs["entries"].clear()
+                graphs["seen"].clear()
 
         def equations(circuit_states, measure_matrices):
             """The per-qubit einsum strings of this signature (index bookkeeping parity)."""
@@ -460,6 +628,8 @@ class B200Strategy(ContractionStrategy):
             return build_schedule(table, nq, sd, mi, right=right_mode, right_table=right_table).equations
 
         compute_fn.loss_and_grads = loss_and_grads
+        compute_fn.enable_cuda_graphs = enable_cuda_graphs
+        compute_fn.graph_stats = graphs
         compute_fn.equations = equations
         compute_fn.plans = plans
         return compute_fn

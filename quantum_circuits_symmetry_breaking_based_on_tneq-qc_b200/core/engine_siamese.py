@@ -114,6 +114,15 @@ class EngineSiamese:
             mats = wrapped
         return mats, out
 
+    def enable_cuda_graphs(self, flag: bool = True) -> None:
+        """Opt in to CUDA-graph replay of the fused training step (no reference counterpart): when
+        contract_with_compiled_strategy_for_gradient is called again with the SAME device buffers
+        (cores updated in place, batches copied into static input buffers) the step's kernels are
+        replayed from a captured graph.  The loss / gradient tensors returned by a replayed step are
+        the graph's output buffers and are overwritten by the next replay with the same operands."""
+        from ..contractor.b200_strategy import set_cuda_graphs
+        set_cuda_graphs(flag)
+
     # ---- compiled contraction (engine_siamese.py:261-554) ---------------------------
     def _compiled(self, qctn, circuit_states_list, measure_input_list, measure_is_matrix, right_qctn):
         states_shape = _shapes(circuit_states_list)

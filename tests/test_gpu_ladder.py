@@ -129,3 +129,46 @@ def test_cfg3_full_size_properties(built_lib):
     # determinism: the same launch twice gives bit-identical gradients
     lf2, gf2 = eng.contract_with_compiled_strategy_for_gradient(q, states, mx)
     assert lf.item() == lf2.item() and all(torch.equal(u, v) for u, v in zip(gf, gf2))
+
+
+def test_cuda_graph_replay(built_lib):
+    """Opt-in CUDA-graph replay of the fused training step: same numbers as the direct launches,
+    follows in-place updates of the cores and new data copied into the same input buffers, and
+    falls back to direct launches when the buffers change."""
+    n, K, B = 24, 3, 500
+    graph = merged_graph(n, K)
+    names, table, nq, cores, states, mxs = make_case(graph, K, B, "float32", seed=3)
+    eng, q = _setup(graph, K, cores)
+    st = [s.to(DEV) for s in states]
+    mx = [_to_dev(m) for m in clone_mx(mxs)]
+    l0, g0 = eng.contract_with_compiled_strategy_for_gradient(q, st, mx)
+    l0, g0 = l0.item(), [g.clone() for g in g0]
+    fn = eng._compiled(q, st, mx, True, "symmetric")
+    eng.enable_cuda_graphs(True)
+    try:
+        for it in range(4):                        # 1: direct, 2: capture, 3+: replay
+            l, g = eng.contract_with_compiled_strategy_for_gradient(q, st, mx)
+            assert l.item() == pytest.approx(l0, rel=1e-6)
+            assert all(torch.equal(a, b) for a, b in zip(g, g0))
+        assert fn.graph_stats["replays"] >= 2
+        # in-place core update and new measurement data in the same buffers
+        with torch.no_grad():
+            q.cores_weights[names[3]].mul_(1.01)
+            for m in mx:
+                m.tensor.mul_(0.97)
+        lr, gr = eng.contract_with_compiled_strategy_for_gradient(q, st, mx)
+        lr, gr = lr.item(), [g.clone() for g in gr]
+        eng.enable_cuda_graphs(False)
+        ld, gd = eng.contract_with_compiled_strategy_for_gradient(q, st, mx)
+        assert lr == pytest.approx(ld.item(), rel=1e-6)
+        assert all(torch.equal(a, b) for a, b in zip(gr, gd))
+        # different buffers: no stale replay
+        eng.enable_cuda_graphs(True)
+        mx2 = [tneq_b200.TNTensor(m.tensor.clone() * 1.1, m.scale, m.log_scale) for m in mx]
+        l2, g2 = eng.contract_with_compiled_strategy_for_gradient(q, st, mx2)
+        eng.enable_cuda_graphs(False)
+        l3, g3 = eng.contract_with_compiled_strategy_for_gradient(q, st, mx2)
+        assert l2.item() == pytest.approx(l3.item(), rel=1e-6)
+        assert all(torch.equal(a, b) for a, b in zip(g2, g3))
+    finally:
+        eng.enable_cuda_graphs(False)
