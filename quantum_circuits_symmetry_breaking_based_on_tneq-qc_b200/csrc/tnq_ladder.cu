@@ -145,7 +145,12 @@ Geometry geometry(int n, long long B, int mode, int sms) {
     Geometry g;
     g.ngroups = (B + D::SPW - 1) / D::SPW;
     const int wmax = mode == 0 ? WARPS_FWD : WARPS_TRAIN;
-    long long wpc = (g.ngroups + sms - 1) / sms;       // spread small batches over all SMs
+    // groups per SM -> number of passes a warp makes -> the fewest warps per CTA that still finish in
+    // that many passes (fewer resident warps run faster: they share the schedulers and shared memory
+    // bandwidth), and small batches spread over all SMs
+    const long long per_sm = (g.ngroups + sms - 1) / sms;
+    const long long passes = (per_sm + wmax - 1) / wmax;
+    long long wpc = (per_sm + passes - 1) / (passes > 0 ? passes : 1);
     g.wpc = (int)(wpc < 1 ? 1 : (wpc > wmax ? wmax : wpc));
     long long grid = (g.ngroups + g.wpc - 1) / g.wpc;
     g.grid = (int)(grid > sms ? sms : grid);
