@@ -144,13 +144,17 @@ Geometry geometry(int n, long long B, int mode, int sms) {
     using D = Dims<K>;
     Geometry g;
     g.ngroups = (B + D::SPW - 1) / D::SPW;
-    const int wmax = mode == 0 ? WARPS_FWD : WARPS_TRAIN;
-    // groups per SM -> number of passes a warp makes -> the fewest warps per CTA that still finish in
-    // that many passes (fewer resident warps run faster: they share the schedulers and shared memory
-    // bandwidth), and small batches spread over all SMs
-    const long long per_sm = (g.ngroups + sms - 1) / sms;
-    const long long passes = (per_sm + wmax - 1) / wmax;
-    long long wpc = (per_sm + passes - 1) / (passes > 0 ? passes : 1);
+    int wmax = mode == 0 ? WARPS_FWD : WARPS_TRAIN;
+    {   // long chains have a bigger constant pool: fewer warps fit next to it
+        int dev = 0, smem_max = 227 * 1024;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const long long per_warp = (long long)sizeof(float) * (mode == 0 ? D::WARP_FWD : D::WARP_TRAIN);
+        const long long fit = ((long long)smem_max - (long long)sizeof(float) * cst_floats<K>(n)) / per_warp;
+        if (fit < wmax) wmax = fit < 1 ? 1 : (int)fit;
+    }
+    // as many warps per CTA as fit (more resident warps hide more latency; measured: trimming the
+    // warp count to balance the passes is slower), small batches spread over all SMs
+    long long wpc = (g.ngroups + sms - 1) / sms;
     g.wpc = (int)(wpc < 1 ? 1 : (wpc > wmax ? wmax : wpc));
     long long grid = (g.ngroups + g.wpc - 1) / g.wpc;
     g.grid = (int)(grid > sms ? sms : grid);

@@ -39,11 +39,13 @@
 #define TNQ_HD __device__ __forceinline__
 #define TNQ_UNROLL _Pragma("unroll")
 #define TNQ_NOUNROLL _Pragma("unroll 1")
+#define TNQ_UNROLL3 _Pragma("unroll 3")
 #else
 #define TNQ_HOSTDEV
 #define TNQ_HD inline
 #define TNQ_UNROLL
 #define TNQ_NOUNROLL
+#define TNQ_UNROLL3
 #endif
 
 namespace tnq_ladder {
@@ -561,7 +563,7 @@ TNQ_HD void phase_c_bwd(const WarpCtx<K>& c, LaneState<K>& st, int lane, const f
     for (int v = 0; v < D::K2; ++v) st.accX[v].zero();
     const float* U = c.U + s * D::USZ;
     float* d = c.D + s * D::SST + fo * D::PITCH;
-    TNQ_NOUNROLL
+    TNQ_NOUNROLL             // (unrolling by 3 was measured: 3 % slower)
     for (int qr = 0; qr < D::K2; ++qr) {
         Vec<K> u[K];         // [i] over p
         TNQ_UNROLL

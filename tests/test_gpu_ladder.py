@@ -42,7 +42,7 @@ def _bound(eng, q, st, mx):
     return next(iter(eng._compiled(q, st, mx, True, "symmetric").plans.values()))
 
 
-@pytest.mark.parametrize("n,K,B", [(3, 3, 4), (5, 3, 100), (24, 3, 50), (9, 2, 333), (24, 2, 64)])
+@pytest.mark.parametrize("n,K,B", [(3, 3, 4), (5, 3, 100), (24, 3, 50), (9, 2, 333), (24, 2, 64), (64, 2, 40)])
 def test_ladder_vs_oracle(n, K, B, built_lib):
     graph = merged_graph(n, K)
     names, table, nq, cores, states, mxs = well_conditioned_case(graph, K, B, "float32", seed=n + K)
