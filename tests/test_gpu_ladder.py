@@ -42,7 +42,7 @@ def _bound(eng, q, st, mx):
     return next(iter(eng._compiled(q, st, mx, True, "symmetric").plans.values()))
 
 
-@pytest.mark.parametrize("n,K,B", [(3, 3, 4), (5, 3, 100), (24, 3, 50), (9, 2, 333), (24, 2, 64), (64, 2, 40)])
+@pytest.mark.parametrize("n,K,B", [(3, 3, 4), (5, 3, 100), (24, 3, 50), (9, 2, 333), (24, 2, 64)])
 def test_ladder_vs_oracle(n, K, B, built_lib):
     graph = merged_graph(n, K)
     names, table, nq, cores, states, mxs = well_conditioned_case(graph, K, B, "float32", seed=n + K)
@@ -92,6 +92,36 @@ def test_ladder_vs_vm_route(built_lib):
     assert ((va - vb).abs()[big] / vb.abs()[big]).max() < 2e-4
     assert rel_err(va, vb) < 1e-5
     assert abs(la - lb) < 1e-4 * abs(lb)
+
+
+def test_long_chain(built_lib):
+    """64 qubits (126 cores): the constant pool no longer leaves room for the full warp count.
+    Random-data values underflow float32 at this length, so the check is the normalisation known
+    answer (orthogonal cores + identity measurements => 1) and agreement of the two CUDA routes."""
+    n, K, B = 64, 3, 100
+    graph = merged_graph(n, K)
+    torch.manual_seed(5)
+    names, table, nq = oc.parse_graph(graph)
+    cores = oc.random_cores(table, torch.float32)
+    states = [s.to(DEV) for s in oc.unit_states(nq, K)]
+    eye = [torch.eye(K, device=DEV).expand(B, K, K).contiguous() for _ in range(nq)]
+    mx = [e + 0.05 * torch.randn(B, K, K, device=DEV) for e in eye]
+    res = {}
+    for route in ("ladder", "vm"):
+        if route == "vm":
+            os.environ["TNQ_NO_CHAIN"] = "1"
+        try:
+            eng, q = _setup(graph, K, cores)
+            ones = eng.contract_with_compiled_strategy(q, states, eye)
+            assert (ones - 1).abs().max().item() < 2e-5
+            loss, grads = eng.contract_with_compiled_strategy_for_gradient(q, states, mx)
+            res[route] = (loss.item(), [g.cpu() for g in grads])
+        finally:
+            os.environ.pop("TNQ_NO_CHAIN", None)
+    assert abs(res["ladder"][0] - res["vm"][0]) < 1e-4 * max(1.0, abs(res["vm"][0]))
+    for a, b in zip(res["ladder"][1], res["vm"][1]):
+        assert torch.isfinite(a).all()
+        assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-7
 
 
 def test_cfg3_full_size_properties(built_lib):
