@@ -20,6 +20,7 @@
 #include <string>
 
 #include "tneq_b200.h"
+#include "tnq_f2.cuh"
 
 extern int tnq_internal_fail(const std::string& msg);
 extern int tnq_internal_cuda_fail(cudaError_t e, const char* what);
@@ -339,6 +340,126 @@ tnq_chain_kernel(const __grid_constant__ ChainArgs a, long long B, const float* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forward values with TWO samples per thread (MODE 0, batch-contiguous measurements).  Every
+// per-sample quantity is a packed pair (sample b0 + lane, sample b0 + 32 + lane) and the whole step
+// runs on fma.rn.f32x2 (SASS FFMA2) with the folded cores as broadcast scalars: plain FFMA issues
+// only every second cycle per scheduler on sm_100 (tools/ffma_rate.cu), which capped the one-sample
+// kernel at 27 TFLOP/s; packed, the sweep is bound by streaming the measurement matrices from HBM.
+// ------------------------------------------------------------------------------------------------
+using tnq_ladder::F2;
+using tnq_ladder::fma2;
+
+template <int K>
+__device__ __forceinline__ void chain_step2(F2 (&env)[K][K], const float* __restrict__ Ls, const F2 (&M)[K][K]) {
+    F2 out[K][K];            // [j][f]
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int f = 0; f < K; ++f) out[j][f] = F2{0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < K; ++h) {
+        F2 T1[K][K];         // [e][f]
+#pragma unroll
+        for (int e = 0; e < K; ++e)
+#pragma unroll
+            for (int f = 0; f < K; ++f) {
+                F2 s{0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < K; ++c) s = fma2(env[h][c], Ls[(c * K + e) * K + f], s);
+                T1[e][f] = s;
+            }
+#pragma unroll
+        for (int g = 0; g < K; ++g)
+#pragma unroll
+            for (int f = 0; f < K; ++f) {
+                F2 t2{0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < K; ++e) t2 = fma2(T1[e][f], M[e][g], t2);
+#pragma unroll
+                for (int j = 0; j < K; ++j) out[j][f] = fma2(t2, Ls[(h * K + g) * K + j], out[j][f]);
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int f = 0; f < K; ++f) env[j][f] = out[j][f];
+}
+
+// 64 samples x K*K floats, contiguous: raw[i] = run[lane + 32 i]
+template <int K>
+__device__ __forceinline__ void fetch_m2(float (&raw)[2 * K * K], const float* __restrict__ base, long long b0, long long B,
+                                         int lane) {
+    const long long total = (B - b0 < 64 ? B - b0 : 64) * (K * K);
+    const float* p = base + b0 * (K * K);
+#pragma unroll
+    for (int i = 0; i < 2 * K * K; ++i) {
+        const int idx = lane + 32 * i;
+        raw[i] = idx < total ? __ldg(p + idx) : 0.f;
+    }
+}
+template <int K>
+__device__ __forceinline__ void unpack_m2(F2 (&M)[K][K], const float (&raw)[2 * K * K], float* slab, int lane) {
+    constexpr int LD = (K * K) | 1;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 2 * K * K; ++i) {
+        const int idx = lane + 32 * i;
+        slab[(idx / (K * K)) * LD + idx % (K * K)] = raw[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) M[i][j] = F2{slab[lane * LD + i * K + j], slab[(lane + 32) * LD + i * K + j]};
+}
+
+template <int K>
+__global__ void __launch_bounds__(CHAIN_THREADS)
+tnq_chain_fwd2_kernel(const __grid_constant__ ChainArgs a, long long B, float* __restrict__ values) {
+    constexpr int K3 = K * K * K;
+    extern __shared__ float sm[];
+    const int n = a.n;
+    float* Ls = sm;                                   // [n-1][K3]
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int SLAB = 64 * ((K * K) | 1);
+    float* slab = sm + (n - 1) * K3 + warp * SLAB;
+    for (int i = threadIdx.x; i < (n - 1) * K3; i += blockDim.x) {
+        const int q = i / K3, r = i % K3, c = r / (K * K), e = (r / K) % K, f = r % K;
+        float s = 0.f;
+        for (int d = 0; d < K; ++d) s = fmaf(__ldg(a.core[q] + ((c * K + d) * K + e) * K + f), __ldg(a.state[q + 1] + d), s);
+        Ls[i] = s;
+    }
+    __syncthreads();
+    float s0[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) s0[i] = __ldg(a.state[0] + i);
+    const long long ntiles = (B + 63) / 64;
+    for (long long wi = (long long)blockIdx.x * warps + warp; wi < ntiles; wi += (long long)gridDim.x * warps) {
+        const long long b0 = wi * 64;
+        F2 env[K][K], M[K][K];
+#pragma unroll
+        for (int h = 0; h < K; ++h)
+#pragma unroll
+            for (int c = 0; c < K; ++c) env[h][c] = F2{s0[h] * s0[c], s0[h] * s0[c]};
+        float raw[2 * K * K];
+        fetch_m2<K>(raw, a.mx[0], b0, B, lane);
+        unpack_m2<K>(M, raw, slab, lane);
+        for (int q = 0; q < n - 1; ++q) {
+            fetch_m2<K>(raw, a.mx[q + 1], b0, B, lane);   // next qubit's Mx in flight during this step
+            chain_step2<K>(env, Ls + q * K3, M);
+            unpack_m2<K>(M, raw, slab, lane);
+        }
+        F2 val{0.f, 0.f};                              // "acd,adc->a"
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int d = 0; d < K; ++d) val = fma2(env[c][d], M[d][c], val);
+        if (b0 + lane < B) values[b0 + lane] = val.lo;
+        if (b0 + 32 + lane < B) values[b0 + 32 + lane] = val.hi;
+    }
+}
+
 // dG_q[c,d,e,f] = dLs_q[c,e,f] * s_{q+1}[d] ; loss
 template <int K>
 __global__ void tnq_chain_finalize_kernel(const __grid_constant__ ChainArgs a, const float* __restrict__ partials, int nparts,
@@ -375,6 +496,21 @@ int launch_chain(const ChainArgs& a, long long B, int mode, const float* seed, f
         return tnq_internal_fail("tnq_mps_chain: workspace too small");
     const float inv = 1.0f / (float)B;
     cudaError_t e = cudaSuccess;
+    bool packed = true;
+    for (int q = 0; q < a.n; ++q) packed = packed && (a.mx_stride[q] == K * K);
+    if (mode == 0 && packed) {   // two samples per thread, packed FFMA2
+        const size_t smem2 = sizeof(float) * ((size_t)(a.n - 1) * K3 + (size_t)warps * 64 * ((K * K) | 1));
+        long long want2 = (B + 2 * CHAIN_THREADS - 1) / (2 * CHAIN_THREADS);
+        const long long cap2 = (long long)sms * 4;
+        const int grid2 = (int)(want2 < 1 ? 1 : (want2 > cap2 ? cap2 : want2));
+        if (smem2 > 48 * 1024) e = cudaFuncSetAttribute(tnq_chain_fwd2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(chain fwd2)");
+        tnq_chain_fwd2_kernel<K><<<grid2, CHAIN_THREADS, smem2, st>>>(a, B, values);
+        tnq_internal_count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_mps_chain launch");
+        return 0;
+    }
     if (mode == 0) {
         if (smem > 48 * 1024) e = cudaFuncSetAttribute(tnq_chain_kernel<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         tnq_chain_kernel<K, 0><<<grid, CHAIN_THREADS, smem, st>>>(a, B, seed, values, partials, log_scale, inv);

@@ -95,33 +95,43 @@ def test_ladder_vs_vm_route(built_lib):
 
 
 def test_long_chain(built_lib):
-    """64 qubits (126 cores): the constant pool no longer leaves room for the full warp count.
-    Random-data values underflow float32 at this length, so the check is the normalisation known
-    answer (orthogonal cores + identity measurements => 1) and agreement of the two CUDA routes."""
-    n, K, B = 64, 3, 100
-    graph = merged_graph(n, K)
-    torch.manual_seed(5)
-    names, table, nq = oc.parse_graph(graph)
-    cores = oc.random_cores(table, torch.float32)
-    states = [s.to(DEV) for s in oc.unit_states(nq, K)]
-    eye = [torch.eye(K, device=DEV).expand(B, K, K).contiguous() for _ in range(nq)]
-    mx = [e + 0.05 * torch.randn(B, K, K, device=DEV) for e in eye]
-    res = {}
-    for route in ("ladder", "vm"):
-        if route == "vm":
-            os.environ["TNQ_NO_CHAIN"] = "1"
-        try:
-            eng, q = _setup(graph, K, cores)
-            ones = eng.contract_with_compiled_strategy(q, states, eye)
-            assert (ones - 1).abs().max().item() < 2e-5
-            loss, grads = eng.contract_with_compiled_strategy_for_gradient(q, states, mx)
-            res[route] = (loss.item(), [g.cpu() for g in grads])
-        finally:
-            os.environ.pop("TNQ_NO_CHAIN", None)
-    assert abs(res["ladder"][0] - res["vm"][0]) < 1e-4 * max(1.0, abs(res["vm"][0]))
-    for a, b in zip(res["ladder"][1], res["vm"][1]):
-        assert torch.isfinite(a).all()
-        assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-7
+    """Long chains.  Random-data values underflow float32 at these lengths, so the checks are the
+    normalisation known answer (orthogonal cores + identity measurements => 1), agreement of the two
+    CUDA routes at 40 qubits (the VM's operand table ends at 192 inputs), and at 64 qubits -- where
+    the constant pool no longer leaves room for the full warp count -- batch-split consistency."""
+    K, B = 3, 100
+    for n, against_vm in ((40, True), (64, False)):
+        graph = merged_graph(n, K)
+        torch.manual_seed(5)
+        names, table, nq = oc.parse_graph(graph)
+        cores = oc.random_cores(table, torch.float32)
+        states = [s.to(DEV) for s in oc.unit_states(nq, K)]
+        eye = [torch.eye(K, device=DEV).expand(B, K, K).contiguous() for _ in range(nq)]
+        mx = [e + 0.05 * torch.randn(B, K, K, device=DEV) for e in eye]
+        res = {}
+        for route in ("ladder", "vm") if against_vm else ("ladder",):
+            if route == "vm":
+                os.environ["TNQ_NO_CHAIN"] = "1"
+            try:
+                eng, q = _setup(graph, K, cores)
+                ones = eng.contract_with_compiled_strategy(q, states, eye)
+                assert (ones - 1).abs().max().item() < 2e-5
+                loss, grads = eng.contract_with_compiled_strategy_for_gradient(q, states, mx)
+                res[route] = (loss.item(), [g.cpu() for g in grads])
+                if not against_vm:
+                    la, ga = eng.contract_with_compiled_strategy_for_gradient(q, states, [m[:37] for m in mx])
+                    lb, gb = eng.contract_with_compiled_strategy_for_gradient(q, states, [m[37:] for m in mx])
+                    assert abs(loss.item() - (0.37 * la.item() + 0.63 * lb.item())) < 1e-5 * max(1.0, abs(loss.item()))
+                    for f, u, v in zip(grads, ga, gb):
+                        mix = 0.37 * u + 0.63 * v
+                        assert torch.isfinite(f).all()
+                        assert (f - mix).abs().max().item() <= 2e-4 * mix.abs().max().item() + 1e-7
+            finally:
+                os.environ.pop("TNQ_NO_CHAIN", None)
+        if against_vm:
+            assert abs(res["ladder"][0] - res["vm"][0]) < 1e-4 * max(1.0, abs(res["vm"][0]))
+            for a, b in zip(res["ladder"][1], res["vm"][1]):
+                assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-7
 
 
 def test_cfg3_full_size_properties(built_lib):
