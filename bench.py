@@ -312,15 +312,18 @@ def main():
     # EngineSiamese.enable_cuda_graphs) filled from pinned host memory on a copy stream; the copy of
     # batch i+1 is issued before the contraction of batch i and awaited before the step ends, so
     # every timed step contains one full H2D of a batch (overlapped with compute) and the D2H of the loss
-    mx_static = [[torch.empty_like(m.tensor) for m in mx_dev] for _ in range(2)]
+    # (the batch lives in ONE pinned (n, B, K, K) host tensor and one device tensor per slot, so a
+    # step's input is a single cudaMemcpyAsync; the engine gets the per-qubit views it expects)
+    host_all = torch.stack(mx_host, 0).pin_memory()
+    dev_all = [torch.empty_like(host_all, device=dev) for _ in range(2)]
+    mx_static = [[d[q] for q in range(nq)] for d in dev_all]
     copy_stream = torch.cuda.Stream(device=dev)
     pipe = {"i": 0, "ready": None}
 
     def issue_copy(slot):
         copy_stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(copy_stream):
-            for d, h in zip(mx_static[slot], mx_host):
-                d.copy_(h, non_blocking=True)
+            dev_all[slot].copy_(host_all, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return ev
