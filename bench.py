@@ -194,6 +194,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="do not replay the training step from a CUDA graph")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="average gradients with NCCL instead of the one-shot NVLink kernel (tnq_allreduce_oneshot)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -296,13 +298,28 @@ def main():
     train = wl["mode"] == "train"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    # gradient + loss averaging: ONE exchange per step.  Small messages (15 KB for cfg3) go through this
+    # repository's one-shot NVLink kernel over symmetric memory; big ones (cfg4: GBs) through NCCL.
+    oneshot = None
+    n_grad = sum(v.numel() for v in cores_cpu.values())
+    if dist is not None and train and esz == 4 and n_grad < (1 << 18) and not args.nccl_allreduce:
+        from tneq_b200.distributed.oneshot import OneShotAllReduce
+        oneshot = OneShotAllReduce.create(n_grad + 16, dev)
+
+    def average(loss, grads):
+        base = grads[0]._base if len(grads) else None
+        if oneshot is not None and base is not None and base.numel() == n_grad and base.is_contiguous():
+            return oneshot.mean(base, loss.reshape(1))
+        flat = torch.cat([g.reshape(-1) for g in grads] + [loss.reshape(1)])
+        dist.all_reduce(flat)
+        flat /= world
+        return flat
+
     def step_device():
         if train:
             loss, grads, _vals, _sc = fn.loss_and_grads(cores_dict, states, mx_dev)
             if dist is not None:
-                flat = torch.cat([g.reshape(-1) for g in grads] + [loss.reshape(1)])
-                dist.all_reduce(flat)
-                flat /= world
+                average(loss, grads)
             return loss
         with torch.no_grad():
             return fn(cores_dict, states, mx_dev).tensor
@@ -338,10 +355,7 @@ def main():
         if train:
             loss, grads = engine.contract_with_compiled_strategy_for_gradient(qctn, states, mxs)
             if dist is not None:
-                flat = torch.cat([g.reshape(-1) for g in grads] + [loss.reshape(1)])
-                dist.all_reduce(flat)
-                flat /= world
-                val = float(flat[-1].item())
+                val = float(average(loss, grads)[-1].item())
             else:
                 val = float(loss.item())
         else:
@@ -485,7 +499,9 @@ def main():
                        "cores": len(names), "l2": "flushed between timed steps (256 MiB write)",
                        "cuda_graphs": bool(train and not args.no_graphs),
                        "parallelism": f"batch sharded over {world} GPU(s); cores replicated; "
-                                      + ("one packed NCCL all-reduce of grads+loss per step" if world > 1 else "no collective")},
+                                      + (("one one-shot NVLink all-reduce (tnq_allreduce_oneshot, symmetric memory) of grads+loss per step"
+                                          if oneshot is not None else "one packed NCCL all-reduce of grads+loss per step")
+                                         if world > 1 else "no collective")},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
     if e2e is not None:
         line["e2e"] = e2e

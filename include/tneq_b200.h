@@ -163,6 +163,20 @@ int tnq_cplx_fold_f32(const float* in, float* out, int ndim, const int64_t* out_
 int tnq_sgdg_step(float* const* params, const float* const* grads, float* const* velocity, const int* rows,
                   const int* cols, int ncores, int max_cols, float lr, float momentum, void* stream);
 
+/*
+ * One-shot all-reduce of the packed gradient + loss buffer of one training step over NVLink peer
+ * memory (replaces the per-core blocking collectives of DataParallelTrainer.sync_gradients,
+ * tneq_qc/distributed/parallel/data_parallel.py:194-204 / comm/comm_torch.py:292-318).
+ *   peer_bufs_dev : DEVICE array of `world` pointers, entry r = rank r's symmetric buffer as mapped
+ *                   into this process (torch.distributed._symmetric_memory: buffer_ptrs_dev); every
+ *                   buffer has tnq_allreduce_oneshot_words(nmax) zero-initialised 32-bit words
+ *   out[0, na+nb) = scale * sum over ranks of (src_a[0,na) ++ src_b[0,nb)), summed in rank order on
+ *   every rank (bit-identical results).  All ranks must call it the same number of times.
+ */
+int64_t tnq_allreduce_oneshot_words(int64_t nmax);
+int tnq_allreduce_oneshot(const uint64_t* peer_bufs_dev, int rank, int world, int64_t nmax, const float* src_a,
+                          int64_t na, const float* src_b, int64_t nb, float* out, float scale, void* stream);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t tnq_launch_count(void);
 
