@@ -75,6 +75,7 @@ class DataParallelTrainer:
         self.stats = TrainingStats()
         self.accumulated_grads: Optional[List[torch.Tensor]] = None
         self.accumulation_count = 0
+        self._oneshot, self._oneshot_tried = None, False
         random.seed(self.config.seed)          # lock-step QR retractions on every rank
 
     def _log(self, msg: str, level: str = "info"):
@@ -110,10 +111,35 @@ class DataParallelTrainer:
     def sync_loss(self, local_loss: float) -> float:
         return self.comm.allreduce_scalar(float(local_loss), op=ReduceOp.AVG)
 
+    def _oneshot_for(self, n_grad: int, device) -> Optional[object]:
+        """The one-shot NVLink all-reduce (csrc/tnq_allreduce.cu) for small float32 messages on NCCL
+        process groups; None when symmetric memory is unavailable (the NCCL path is used then)."""
+        if self._oneshot is None and not self._oneshot_tried:
+            self._oneshot_tried = True
+            if self.comm.backend == "nccl" and self.world_size > 1 and n_grad < (1 << 18):
+                from .oneshot import OneShotAllReduce
+                self._oneshot = OneShotAllReduce.create(n_grad + 16, device)
+        return self._oneshot
+
     def sync_gradients_and_loss(self, grads: List[torch.Tensor], loss) -> Tuple[List[torch.Tensor], torch.Tensor]:
-        """Gradients and loss in ONE collective."""
+        """Gradients and loss in ONE exchange: this repository's one-shot NVLink kernel when the
+        gradients sit in one flat float32 buffer (the fused CUDA routes return them that way), else one
+        packed NCCL all-reduce."""
         loss_t = loss if isinstance(loss, torch.Tensor) else torch.tensor(float(loss), device=grads[0].device)
         loss_t = loss_t.detach().reshape(1).to(grads[0].real.dtype if grads[0].is_complex() else grads[0].dtype)
+        base = getattr(grads[0], "_base", None) if len(grads) else None
+        n_grad = sum(g.numel() for g in grads)
+        if (base is not None and base.is_cuda and base.dtype == torch.float32 and base.is_contiguous()
+                and base.numel() == n_grad and all(getattr(g, "_base", None) is base for g in grads)
+                and loss_t.dtype == torch.float32):
+            red = self._oneshot_for(n_grad, base.device)
+            if red is not None and n_grad + 1 <= red.nmax:
+                out = red.mean(base, loss_t)
+                pieces, at = [], 0
+                for g in grads:
+                    pieces.append(out[at:at + g.numel()].reshape(g.shape))
+                    at += g.numel()
+                return pieces, out[-1]
         out = self.comm.allreduce_list(list(grads) + [loss_t], op=ReduceOp.AVG)
         return out[:-1], out[-1][0]
 
