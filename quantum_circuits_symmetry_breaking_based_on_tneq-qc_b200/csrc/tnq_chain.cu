@@ -460,6 +460,182 @@ tnq_chain_fwd2_kernel(const __grid_constant__ ChainArgs a, long long B, float* _
     }
 }
 
+// Training / seeded reverse sweep with TWO samples per thread (MODE 1 / 2, batch-contiguous
+// measurements, K <= 3): the same packed arithmetic as tnq_chain_fwd2_kernel for the forward sweep
+// (left environments taped in local memory) and for the reverse sweep, whose per-h slices keep the
+// working set in registers.  A thread's two gradient contributions are added before the warp
+// reduction, so the shuffle tree runs once per 64 samples instead of once per 32.
+template <int K, int MODE>
+__global__ void __launch_bounds__(CHAIN_THREADS)
+tnq_chain_train2_kernel(const __grid_constant__ ChainArgs a, long long B, const float* __restrict__ seed,
+                        float* __restrict__ values, float* __restrict__ partials, float log_scale, float inv_count) {
+    constexpr int K3 = K * K * K;
+    extern __shared__ float sm[];
+    const int n = a.n;
+    float* Ls = sm;
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int SLAB = 64 * ((K * K) | 1);
+    float* slab = sm + (n - 1) * K3 + warp * SLAB;
+    float* wacc = sm + (n - 1) * K3 + warps * SLAB;   // [warps][(n-1) * K3 + 1]
+    const int acc_stride = (n - 1) * K3 + 1;
+    for (int i = threadIdx.x; i < (n - 1) * K3; i += blockDim.x) {
+        const int q = i / K3, r = i % K3, c = r / (K * K), e = (r / K) % K, f = r % K;
+        float s = 0.f;
+        for (int d = 0; d < K; ++d) s = fmaf(__ldg(a.core[q] + ((c * K + d) * K + e) * K + f), __ldg(a.state[q + 1] + d), s);
+        Ls[i] = s;
+    }
+    for (int i = threadIdx.x; i < warps * acc_stride; i += blockDim.x) wacc[i] = 0.f;
+    __syncthreads();
+    float s0[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) s0[i] = __ldg(a.state[0] + i);
+    float* my_acc = wacc + warp * acc_stride;
+    const long long ntiles = (B + 63) / 64;
+    for (long long wi = (long long)blockIdx.x * warps + warp; wi < ntiles; wi += (long long)gridDim.x * warps) {
+        const long long b0 = wi * 64;
+        const bool vlo = b0 + lane < B, vhi = b0 + 32 + lane < B;
+        F2 env[K][K], M[K][K];
+#pragma unroll
+        for (int h = 0; h < K; ++h)
+#pragma unroll
+            for (int c = 0; c < K; ++c) env[h][c] = F2{s0[h] * s0[c], s0[h] * s0[c]};
+        F2 tape[MAXQ][K][K];
+        float raw[2 * K * K];
+        fetch_m2<K>(raw, a.mx[0], b0, B, lane);
+        unpack_m2<K>(M, raw, slab, lane);
+        for (int q = 0; q < n - 1; ++q) {
+#pragma unroll
+            for (int h = 0; h < K; ++h)
+#pragma unroll
+                for (int c = 0; c < K; ++c) tape[q][h][c] = env[h][c];
+            fetch_m2<K>(raw, a.mx[q + 1], b0, B, lane);
+            chain_step2<K>(env, Ls + q * K3, M);
+            unpack_m2<K>(M, raw, slab, lane);
+        }
+        F2 val{0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int d = 0; d < K; ++d) val = fma2(env[c][d], M[d][c], val);
+        if (MODE != 2 && values != nullptr) {
+            if (vlo) values[b0 + lane] = val.lo;
+            if (vhi) values[b0 + 32 + lane] = val.hi;
+        }
+        // ---- seed ----
+        F2 dval;
+        if (MODE == 1) {
+            const float clo = fmaxf(val.lo, 1e-10f), chi = fmaxf(val.hi, 1e-10f);
+            float lpart = (vlo ? -(logf(clo) + log_scale) * inv_count : 0.f) + (vhi ? -(logf(chi) + log_scale) * inv_count : 0.f);
+            lpart = warp_sum(lpart);
+            if (lane == 0) my_acc[acc_stride - 1] += lpart;
+            dval = F2{(vlo && val.lo >= 1e-10f) ? -inv_count / clo : 0.f, (vhi && val.hi >= 1e-10f) ? -inv_count / chi : 0.f};
+        } else {
+            dval = F2{vlo ? __ldg(seed + b0 + lane) : 0.f, vhi ? __ldg(seed + b0 + 32 + lane) : 0.f};
+        }
+        F2 denv[K][K];
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int d = 0; d < K; ++d) denv[c][d] = F2{dval.lo * M[d][c].lo, dval.hi * M[d][c].hi};
+        // ---- reverse sweep ----
+        fetch_m2<K>(raw, a.mx[n - 2], b0, B, lane);
+        for (int q = n - 2; q >= 0; --q) {
+            const float* L = Ls + q * K3;
+            unpack_m2<K>(M, raw, slab, lane);
+            if (q > 0) fetch_m2<K>(raw, a.mx[q - 1], b0, B, lane);
+            float* gq = my_acc + q * K3;
+            F2 accL[K][K][K];    // [c][e][f]: sum_h e0[h][c] dT1[h][e][f], both samples
+            F2 dnew[K][K];       // [h][c]
+#pragma unroll
+            for (int c = 0; c < K; ++c)
+#pragma unroll
+                for (int e = 0; e < K; ++e)
+#pragma unroll
+                    for (int f = 0; f < K; ++f) accL[c][e][f] = F2{0.f, 0.f};
+#pragma unroll
+            for (int h = 0; h < K; ++h) {
+                F2 e0[K];
+#pragma unroll
+                for (int c = 0; c < K; ++c) e0[c] = tape[q][h][c];
+                F2 T1[K][K], T2[K][K];   // [e][f], [g][f]
+#pragma unroll
+                for (int e = 0; e < K; ++e)
+#pragma unroll
+                    for (int f = 0; f < K; ++f) {
+                        F2 t{0.f, 0.f};
+#pragma unroll
+                        for (int c = 0; c < K; ++c) t = fma2(e0[c], L[(c * K + e) * K + f], t);
+                        T1[e][f] = t;
+                    }
+#pragma unroll
+                for (int g = 0; g < K; ++g)
+#pragma unroll
+                    for (int f = 0; f < K; ++f) {
+                        F2 t{0.f, 0.f};
+#pragma unroll
+                        for (int e = 0; e < K; ++e) t = fma2(T1[e][f], M[e][g], t);
+                        T2[g][f] = t;
+                    }
+                // R role: dLs[h][g][j] += sum_f T2[g][f] denv[j][f] ; dT2[g][f] = sum_j denv[j][f] Ls[h][g][j]
+#pragma unroll
+                for (int g = 0; g < K; ++g) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        F2 t{0.f, 0.f};
+#pragma unroll
+                        for (int f = 0; f < K; ++f) t = fma2(T2[g][f], denv[j][f], t);
+                        const float sred = warp_sum(t.lo + t.hi);
+                        if (lane == 0) gq[(h * K + g) * K + j] += sred;
+                    }
+#pragma unroll
+                    for (int f = 0; f < K; ++f) {
+                        F2 t{0.f, 0.f};
+#pragma unroll
+                        for (int j = 0; j < K; ++j) t = fma2(denv[j][f], L[(h * K + g) * K + j], t);
+                        T2[g][f] = t;                      // now dT2
+                    }
+                }
+                // dT1[e][f] = sum_g dT2[g][f] M[e][g] ; L role: accL[c][e][f] += e0[c] dT1[e][f] ;
+                // dnew[h][c] = sum_{e,f} dT1[e][f] Ls[c][e][f]
+#pragma unroll
+                for (int c = 0; c < K; ++c) dnew[h][c] = F2{0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < K; ++e)
+#pragma unroll
+                    for (int f = 0; f < K; ++f) {
+                        F2 d1{0.f, 0.f};
+#pragma unroll
+                        for (int g = 0; g < K; ++g) d1 = fma2(T2[g][f], M[e][g], d1);
+#pragma unroll
+                        for (int c = 0; c < K; ++c) {
+                            accL[c][e][f] = fma2(e0[c], d1, accL[c][e][f]);
+                            dnew[h][c] = fma2(d1, L[(c * K + e) * K + f], dnew[h][c]);
+                        }
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < K; ++c)
+#pragma unroll
+                for (int e = 0; e < K; ++e)
+#pragma unroll
+                    for (int f = 0; f < K; ++f) {
+                        const float sred = warp_sum(accL[c][e][f].lo + accL[c][e][f].hi);
+                        if (lane == 0) gq[(c * K + e) * K + f] += sred;
+                    }
+#pragma unroll
+            for (int h = 0; h < K; ++h)
+#pragma unroll
+                for (int c = 0; c < K; ++c) denv[h][c] = dnew[h][c];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < acc_stride; i += blockDim.x) {
+        float sacc = 0.f;
+        for (int w = 0; w < warps; ++w) sacc += wacc[w * acc_stride + i];
+        partials[(size_t)blockIdx.x * acc_stride + i] = sacc;
+    }
+}
+
 // dG_q[c,d,e,f] = dLs_q[c,e,f] * s_{q+1}[d] ; loss
 template <int K>
 __global__ void tnq_chain_finalize_kernel(const __grid_constant__ ChainArgs a, const float* __restrict__ partials, int nparts,
@@ -510,6 +686,28 @@ int launch_chain(const ChainArgs& a, long long B, int mode, const float* seed, f
         e = cudaGetLastError();
         if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_mps_chain launch");
         return 0;
+    }
+    if constexpr (K <= 3) {
+        if (mode != 0 && packed) {   // two samples per thread, packed FFMA2 (forward tape + reverse sweep)
+            const size_t smem2 = sizeof(float) * ((size_t)(a.n - 1) * K3 + (size_t)warps * 64 * ((K * K) | 1) +
+                                                  (size_t)warps * acc_stride);
+            long long want2 = (B + 2 * CHAIN_THREADS - 1) / (2 * CHAIN_THREADS);
+            const int grid2 = (int)(want2 < 1 ? 1 : (want2 > cap ? cap : want2));   // same bound as the workspace
+            if (mode == 1) {
+                if (smem2 > 48 * 1024) e = cudaFuncSetAttribute(tnq_chain_train2_kernel<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                tnq_chain_train2_kernel<K, 1><<<grid2, CHAIN_THREADS, smem2, st>>>(a, B, seed, values, partials, log_scale, inv);
+            } else {
+                if (smem2 > 48 * 1024) e = cudaFuncSetAttribute(tnq_chain_train2_kernel<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                tnq_chain_train2_kernel<K, 2><<<grid2, CHAIN_THREADS, smem2, st>>>(a, B, seed, values, partials, log_scale, inv);
+            }
+            if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(chain train2)");
+            tnq_internal_count_launch();
+            tnq_chain_finalize_kernel<K><<<(acc_stride + 127) / 128, 128, 0, st>>>(a, partials, grid2, mode == 1 ? loss : nullptr);
+            tnq_internal_count_launch();
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_mps_chain launch");
+            return 0;
+        }
     }
     if (mode == 0) {
         if (smem > 48 * 1024) e = cudaFuncSetAttribute(tnq_chain_kernel<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
