@@ -23,7 +23,7 @@ namespace {
 
 using namespace tnq_ladder;
 
-constexpr int WARPS_FWD = 12;     // warps per CTA, forward only (one CTA per SM)
+constexpr int WARPS_FWD = 16;     // warps per CTA, forward only (one CTA per SM, 128 registers per thread)
 constexpr int WARPS_TRAIN = 8;    // with the reverse sweep: registers are allocated in units of 4 warps (8 x 32 x 255 <= 64 K)
 
 template <int K>
@@ -32,7 +32,7 @@ __host__ __device__ constexpr int cst_floats(int n) {
 }
 
 template <int K, int MODE>
-__global__ void __maxnreg__(MODE == 0 ? 168 : 255)
+__global__ void __maxnreg__(MODE == 0 ? 128 : 255)
 tnq_ladder_kernel(const __grid_constant__ Args a, long long B, long long ngroups, const float* __restrict__ seed,
                   float* __restrict__ values, float* __restrict__ gparts, float* __restrict__ lparts,
                   float* __restrict__ ckpt, float log_scale, float inv_count) {
