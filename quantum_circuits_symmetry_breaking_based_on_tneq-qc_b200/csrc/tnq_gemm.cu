@@ -24,6 +24,7 @@
 //                          the stage's "empty" mbarrier; owns the TMEM allocation (128 columns).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -143,11 +144,18 @@ __device__ __forceinline__ void store_unit(float4 v, int unit, int lane, uint32_
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_base + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
 }
 
-template <bool ALIGNED>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// SMALLK (K <= 256: a handful of k-blocks, the regime of the bond-64 sweep where K = 2 x bond):
+// one pipeline stage, 2 accumulators (hi*hi + correction) = 256 TMEM columns and <= 112 registers,
+// so that TWO CTAs share an SM and one tile's epilogue overlaps the other tile's loads and MMAs --
+// with a single resident CTA the tensor core idles through every prologue and epilogue.
+template <bool ALIGNED, bool SMALLK>
+__global__ void __launch_bounds__(GEMM_THREADS, SMALLK ? 2 : 1)
 tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, long long M,
                        long long N, long long K, long long lda, long long ldb, long long ldc, long long strideA,
                        long long strideB, long long strideC, int accumulate) {
+    constexpr int NSTAGE = SMALLK ? 1 : STAGES;
+    constexpr int NACC = SMALLK ? 1 : 3;                 // round-robin hi*hi accumulators; the correction one follows
+    constexpr uint32_t NCOLS = SMALLK ? 256u : TMEM_COLS;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[2 * STAGES + 1];
     __shared__ uint32_t tmem_base_slot;
@@ -159,7 +167,7 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(full0 + 8 * s, PRODUCERS);
             mbar_init(empty0 + 8 * s, 1);
         }
@@ -168,7 +176,7 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
     }
     if (warp == PRODUCERS / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                     "r"(TMEM_COLS)
+                     "r"(NCOLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -181,8 +189,8 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
     if (warp < PRODUCERS / 32) {
         // ---------------- producers ----------------
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+            const int s = kb % NSTAGE;
+            const uint32_t phase = (uint32_t)(kb / NSTAGE) & 1u;
             mbar_wait(empty0 + 8 * s, phase ^ 1u);
             const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
             const long long k0 = (long long)kb * BK;
@@ -226,8 +234,8 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
 #pragma unroll 1
-            for (int extra = 1; extra < 4; ++extra) {
-                if (extra < 3 && nkb * (BK / 8) <= extra) continue;   // that accumulator was never written
+            for (int extra = 1; extra <= NACC; ++extra) {
+                if (extra < NACC && nkb * (BK / 8) <= extra) continue;   // that accumulator was never written
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -261,8 +269,8 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
     } else {
         // ---------------- MMA issuer ----------------
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+            const int s = kb % NSTAGE;
+            const uint32_t phase = (uint32_t)(kb / NSTAGE) & 1u;
             mbar_wait(full0 + 8 * s, phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
@@ -280,9 +288,9 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
                     // The hi*hi products themselves are spread round-robin over three accumulators,
                     // which cuts the length of every truncating chain by three.
                     const int step = kb * (BK / 8) + j;
-                    umma_tf32(tmem_base + 3 * BN, a_lo, b_hi, step != 0);
-                    umma_tf32(tmem_base + 3 * BN, a_hi, b_lo, 1u);
-                    umma_tf32(tmem_base + (uint32_t)(step % 3) * BN, a_hi, b_hi, step >= 3);
+                    umma_tf32(tmem_base + NACC * BN, a_lo, b_hi, step != 0);
+                    umma_tf32(tmem_base + NACC * BN, a_hi, b_lo, 1u);
+                    umma_tf32(tmem_base + (uint32_t)(step % NACC) * BN, a_hi, b_hi, step >= NACC);
                 }
                 umma_commit(empty0 + 8 * s);                          // frees the stage when the MMAs retire
                 if (kb == nkb - 1) umma_commit(accum_bar);            // accumulator complete
@@ -292,7 +300,7 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
     }
     __syncthreads();
     if (warp == PRODUCERS / 32) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NCOLS) : "memory");
     }
 }
 
@@ -305,8 +313,10 @@ extern "C" int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t
     const bool aligned = !((K & 3) || (lda & 3) || (ldb & 3) || (strideA & 3) || (strideB & 3) || ((uintptr_t)A & 15) ||
                            ((uintptr_t)B & 15));
     if (batch > 65535) return tnq_internal_fail("tnq_gemm_tf32x3: batch too large for one launch (max 65535)");
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-    auto kern = aligned ? tnq_gemm_tf32x3_kernel<true> : tnq_gemm_tf32x3_kernel<false>;
+    const bool smallk = K <= 256 && !getenv("TNQ_GEMM_NO_SMALLK");
+    const size_t smem = (size_t)(smallk ? 1 : STAGES) * STAGE_BYTES + 1024;
+    auto kern = smallk ? (aligned ? tnq_gemm_tf32x3_kernel<true, true> : tnq_gemm_tf32x3_kernel<false, true>)
+                       : (aligned ? tnq_gemm_tf32x3_kernel<true, false> : tnq_gemm_tf32x3_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(gemm)");
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
