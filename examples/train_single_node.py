@@ -48,6 +48,9 @@ def main():
         graph = tb.QCTN.merge(one, one).graph
     qctn = tb.QCTN(graph, backend=backend)
     print(f"backend {backend.get_backend_name()} on {dev}; {qctn.nqubits} qubits, {len(qctn.cores)} cores")
+    for name in qctn.cores:                      # as in the reference script: cores are trainable once flagged
+        w = qctn.cores_weights[name]
+        (w.tensor if isinstance(w, tb.TNTensor) else w).requires_grad_(True)
 
     tdt = getattr(torch, args.dtype)
     states = [torch.zeros(args.K, device=dev, dtype=tdt) for _ in range(qctn.nqubits)]

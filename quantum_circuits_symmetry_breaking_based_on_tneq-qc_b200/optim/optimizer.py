@@ -78,6 +78,9 @@ class Optimizer:
         """One update of every core, in qctn.cores order (optimizer.py:250-284)."""
         keys = qctn.cores
         params = [qctn.cores_weights[k] for k in keys]
+        if len(grads) != len(params):
+            raise ValueError(f"{len(grads)} gradients for {len(params)} cores: the engine returns gradients only for cores "
+                             "with requires_grad=True (flag every core, as examples/train_single_node.py does)")
         hp = dict(learning_rate=self.learning_rate, beta1=self.beta1, beta2=self.beta2, epsilon=self.epsilon,
                   iter=self.iter, momentum=self.momentum, stiefel=self.stiefel)
         new_params, self.opt_state = self.engine.backend.optimizer_update(params, grads, self.opt_state, self.method, hp)
