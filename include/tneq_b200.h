@@ -162,6 +162,12 @@ int tnq_cplx_fold_f32(const float* in, float* out, int ndim, const int64_t* out_
 #define TNQ_SGDG_MAX_COLS 64
 int tnq_sgdg_step(float* const* params, const float* const* grads, float* const* velocity, const int* rows,
                   const int* cols, int ncores, int max_cols, float lr, float momentum, void* stream);
+/* The same step when parameters, gradients and momentum buffers each live in ONE buffer (the fused
+ * contraction routes return the gradients that way): `offsets` is a DEVICE table [3][ncores] of element
+ * offsets (params | grads | velocity) that is static per network, so a step needs no host-to-device
+ * traffic and no host synchronisation. */
+int tnq_sgdg_step_flat(float* params, const float* grads, float* velocity, const int64_t* offsets, const int* rows,
+                       const int* cols, int ncores, int max_cols, float lr, float momentum, void* stream);
 
 /*
  * One-shot all-reduce of the packed gradient + loss buffer of one training step over NVLink peer

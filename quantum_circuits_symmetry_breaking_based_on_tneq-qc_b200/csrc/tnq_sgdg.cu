@@ -40,7 +40,8 @@ __device__ __forceinline__ void mm(float* C, const float* A, const float* B, int
 
 __global__ void __launch_bounds__(SG_THREADS)
 tnq_sgdg_kernel(float* const* __restrict__ params, const float* const* __restrict__ grads, float* const* __restrict__ vel,
-                const int* __restrict__ rows, const int* __restrict__ cols, int maxd, float lr, float momentum) {
+                const int* __restrict__ rows, const int* __restrict__ cols, int maxd, float lr, float momentum,
+                float* pbase, const float* gbase, float* vbase, const long long* __restrict__ offs) {
     extern __shared__ float sm[];
     const int d = rows[blockIdx.x], D = cols[blockIdx.x];      // p is d x D with d <= D; W is D x D
     const int ld = maxd + 1, sz = maxd * ld;
@@ -48,9 +49,10 @@ tnq_sgdg_kernel(float* const* __restrict__ params, const float* const* __restric
     __shared__ float red[SG_THREADS];
     __shared__ float s_alpha;
     __shared__ int piv;
-    float* p = params[blockIdx.x];
-    const float* g = grads[blockIdx.x];
-    float* v = vel[blockIdx.x];
+    // flat form: three base pointers + a static table of element offsets [3][ncores] (params | grads | velocity)
+    float* p = offs ? pbase + offs[blockIdx.x] : params[blockIdx.x];
+    const float* g = offs ? gbase + offs[gridDim.x + blockIdx.x] : grads[blockIdx.x];
+    float* v = offs ? vbase + offs[2 * gridDim.x + blockIdx.x] : vel[blockIdx.x];
     const float eps = 1e-8f;
     // X (d x D) = row-normalised p ; V (D x d) = momentum * V - g^T
     for (int r = threadIdx.x; r < d; r += blockDim.x) {
@@ -165,9 +167,31 @@ extern "C" int tnq_sgdg_step(float* const* params, const float* const* grads, fl
     cudaError_t e = cudaSuccess;
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(tnq_sgdg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(sgdg)");
-    tnq_sgdg_kernel<<<ncores, SG_THREADS, smem, (cudaStream_t)stream>>>(params, grads, velocity, rows, cols, d, lr, momentum);
+    tnq_sgdg_kernel<<<ncores, SG_THREADS, smem, (cudaStream_t)stream>>>(params, grads, velocity, rows, cols, d, lr, momentum,
+                                                                         nullptr, nullptr, nullptr, nullptr);
     tnq_internal_count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_sgdg_step launch");
+    return 0;
+}
+
+extern "C" int tnq_sgdg_step_flat(float* params, const float* grads, float* velocity, const int64_t* offsets,
+                                  const int* rows, const int* cols, int ncores, int max_cols, float lr, float momentum,
+                                  void* stream) {
+    if (!params || !grads || !velocity || !offsets || !rows || !cols || ncores <= 0)
+        return tnq_internal_fail("tnq_sgdg_step_flat: bad arguments");
+    if (max_cols < 1 || max_cols > TNQ_SGDG_MAX_COLS)
+        return tnq_internal_fail("tnq_sgdg_step_flat: matrix width must be between 1 and " + std::to_string(TNQ_SGDG_MAX_COLS));
+    const int d = max_cols;
+    const size_t smem = sizeof(float) * 7 * (size_t)d * (d + 1);
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(tnq_sgdg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(sgdg)");
+    tnq_sgdg_kernel<<<ncores, SG_THREADS, smem, (cudaStream_t)stream>>>(nullptr, nullptr, nullptr, rows, cols, d, lr, momentum,
+                                                                         params, grads, velocity,
+                                                                         reinterpret_cast<const long long*>(offsets));
+    tnq_internal_count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_sgdg_step_flat launch");
     return 0;
 }

@@ -121,6 +121,60 @@ def _qr_retract(unity):
     return (qm * (torch.sgn(d) if torch.is_complex(d) else torch.sign(d)).unsqueeze(0)).T
 
 
+def _sgdg_flat_step(params, grads, state, lr, mom, out):
+    """All cores in one launch with NO per-step host-to-device traffic: parameters are packed into one
+    fresh buffer (the reference returns new tensors), gradients already sit in one buffer (the fused
+    contraction routes return them as views of it), the momentum buffers live in one persistent
+    buffer, and the offset table is static per network (tnq_sgdg_step_flat).  Returns False when the
+    gradients are not views of one float32 buffer."""
+    from .. import _lib
+    base = getattr(grads[0], "_base", None)
+    if base is None or not base.is_cuda or base.dtype != torch.float32 or not base.is_contiguous():
+        return False
+    b0 = base.data_ptr()
+    g_off = []
+    for g in grads:
+        if getattr(g, "_base", None) is not base or not g.is_contiguous():
+            return False
+        g_off.append((g.data_ptr() - b0) // 4)
+    lib = _lib.load()
+    dev = params[0].device
+    shapes = [_matrix_shape(p.shape) for p in params]
+    sizes = [r * c for r, c in shapes]
+    key = (tuple(shapes), tuple(g_off))
+    with torch.cuda.device(dev):
+        if state.get("_flat_key") != key:          # first step (or a different network): build the static tables
+            p_off = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+            table = np.stack([p_off, np.asarray(g_off, dtype=np.int64), p_off])
+            state["_flat_key"] = key
+            state["_flat_offs"] = torch.from_numpy(table).to(dev)
+            state["_flat_dims"] = torch.tensor([[r for r, _ in shapes], [c for _, c in shapes]], dtype=torch.int32, device=dev)
+            vflat = torch.zeros(int(sum(sizes)), dtype=torch.float32, device=dev)
+            for i, (off, n) in enumerate(zip(p_off, sizes)):
+                old = state["momentum_buffer"][i]
+                r, c = shapes[i]
+                if old is not None:
+                    vflat[off: off + n].copy_(old.reshape(-1))
+                state["momentum_buffer"][i] = vflat[off: off + n].view(c, r)
+            state["_flat_v"] = vflat
+            state["_flat_poff"] = [int(x) for x in p_off]
+        flat = torch.cat([p.reshape(-1) for p in params])
+        p_off = state["_flat_poff"]
+        for n in range(len(params)):
+            # the reference draws one random number per Stiefel core (backend_pytorch.py:382)
+            if random.randint(1, 101) == 1:
+                r, c = shapes[n]
+                x = flat[p_off[n]: p_off[n] + sizes[n]].view(r, c)
+                x.copy_(_qr_retract(x / (torch.norm(x, p=2, dim=1, keepdim=True) + 1e-8)))
+        dims, offs = state["_flat_dims"], state["_flat_offs"]
+        _lib.check(lib.tnq_sgdg_step_flat(flat.data_ptr(), b0, state["_flat_v"].data_ptr(), offs.data_ptr(),
+                                          dims[0].data_ptr(), dims[1].data_ptr(), len(params), max(c for _, c in shapes),
+                                          float(lr), float(mom), torch.cuda.current_stream().cuda_stream))
+    for n, p in enumerate(params):
+        out[n] = flat[p_off[n]: p_off[n] + sizes[n]].view(p.shape)
+    return True
+
+
 def _sgdg_kernel_step(idx, params, grads, state, lr, mom, out):
     """All eligible cores in one launch of tnq_sgdg_step (csrc/tnq_sgdg.cu)."""
     from .. import _lib
@@ -179,6 +233,8 @@ def _sgdg(params, grads, state, hp):
             r, c = _matrix_shape(p.shape)
             if (p.is_cuda and p.dtype == torch.float32 and g.dtype == torch.float32 and 1 <= r <= c <= SGDG_MAX_COLS):
                 fast.append(i)
+    if fast and len(fast) == len(params) and _sgdg_flat_step(params, grads, state, lr, mom, out):
+        return out, state
     if fast:
         _sgdg_kernel_step(fast, params, grads, state, lr, mom, out)
     for i, (p, g) in enumerate(zip(params, grads)):

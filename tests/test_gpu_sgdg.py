@@ -71,6 +71,38 @@ def test_sgdg_kernel_matches_float64_oracle(built_lib, shape, ncores):
         assert (x - y).norm() / y.norm() < TOL
 
 
+def test_sgdg_flat_gradients_take_the_table_free_launch(built_lib):
+    """Gradients that are views of ONE buffer (what the fused contraction routes return) take
+    tnq_sgdg_step_flat: same numbers as the pointer-table launch, over several steps with momentum,
+    fresh parameter tensors every step, one launch per step."""
+    from tneq_b200.optim import steps
+    from tneq_b200 import _lib
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    shape, ncores = (3, 3, 3, 3), 46
+    params = [oc.init_random_core([9, 9], torch.float32).reshape(shape).to(dev) for _ in range(ncores)]
+    pa, pb = [p.clone() for p in params], [p.clone() for p in params]
+    sa, sb = {}, {}
+    hp = dict(learning_rate=0.05, momentum=0.9, stiefel=True)
+    for it in range(5):
+        flat = 0.3 * torch.randn(ncores * 81, device=dev)
+        views = list(flat.view(ncores, *shape).unbind(0))
+        separate = [v.clone() for v in views]
+        random.seed(100 + it)
+        before = _lib.launch_count()
+        old = [p.data_ptr() for p in pa]
+        ga, sa = steps.optimizer_update(list(pa), views, sa, "sgdg", hp)
+        assert _lib.launch_count() == before + 1 and "_flat_offs" in sa
+        random.seed(100 + it)
+        gb, sb = steps.optimizer_update(list(pb), separate, sb, "sgdg", hp)
+        assert "_flat_offs" not in sb
+        for a, b, o in zip(ga, gb, old):
+            assert a.data_ptr() != o and torch.equal(a, b)
+        for a, b in zip(sa["momentum_buffer"], sb["momentum_buffer"]):
+            assert torch.equal(a, b)
+        pa, pb = [g.detach() for g in ga], [g.detach() for g in gb]
+
+
 def test_sgdg_kernel_qr_retraction_and_tntensor(built_lib):
     """The 1 % QR retraction draw stays on the reference's RNG stream; TNTensor params keep their scale."""
     from tneq_b200.optim import steps
