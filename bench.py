@@ -457,7 +457,8 @@ def main():
     kernel_ms = ms_step  # the sweep kernel is >95% of the step (profiles/ ncu launch list)
     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` captures
     # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_ladder_*.txt); cannot be measured live
-    NCU_TRAFFIC = {("cfg3", 16384): 888.6e6 + 1237.3e6, ("cfg3-fwd", 16384): 14.2e6}
+    NCU_TRAFFIC = {("cfg3", 16384): 888.6e6 + 1237.3e6, ("cfg3-fwd", 16384): 14.2e6,
+                   ("cfg2-large", 1 << 20): 604.0e6 + 7.8e6, ("cfg2-train", 1 << 18): 186.3e6 + 74.9e6}
     traffic = NCU_TRAFFIC.get((args.workload, B)) if world == 1 else None
     achieved_tf = flops_launch / (kernel_ms * 1e-3) / 1e12
     hbm = {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9,
@@ -475,7 +476,7 @@ def main():
                     "issued_tf32_tflops": 3 * achieved_tf, "fp32_simt_peak_measured": fp32_peak, "hbm": hbm}
     else:
         roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": achieved_tf / fp32_peak, "traffic": traffic if (bound.ladder and not bound.chain_rank) else None,
+                    "frac": achieved_tf / fp32_peak, "traffic": traffic if (bound.ladder or bound.chain_rank) else None,
                     "peak_source": "measured here: torch.matmul 8192^3 fp32 (TF32 off), best of 5",
                     "kernel": "tnq_chain_kernel" if bound.chain_rank else ("tnq_ladder_kernel" if bound.ladder else "tnq_body_kernel"),
                     "flops_per_launch": flops_launch, "hbm": hbm}
