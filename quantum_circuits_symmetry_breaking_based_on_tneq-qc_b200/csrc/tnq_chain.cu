@@ -415,7 +415,7 @@ __device__ __forceinline__ void unpack_m2(F2 (&M)[K][K], const float (&raw)[2 * 
 }
 
 template <int K>
-__global__ void __launch_bounds__(CHAIN_THREADS)
+__global__ void __launch_bounds__(CHAIN_THREADS, K <= 3 ? 4 : 1)
 tnq_chain_fwd2_kernel(const __grid_constant__ ChainArgs a, long long B, float* __restrict__ values) {
     constexpr int K3 = K * K * K;
     extern __shared__ float sm[];
