@@ -544,7 +544,8 @@ tnq_chain_train2_kernel(const __grid_constant__ ChainArgs a, long long B, const 
             unpack_m2<K>(M, raw, slab, lane);
             if (q > 0) fetch_m2<K>(raw, a.mx[q - 1], b0, B, lane);
             float* gq = my_acc + q * K3;
-            F2 accL[K][K][K];    // [c][e][f]: sum_h e0[h][c] dT1[h][e][f], both samples
+            F2 accL[K][K][K];    // d Ls[c][e][f] of this thread's two samples: L role sum_h e0[h][c] dT1[h][e][f]
+                                 // plus R role sum_f T2[h][g][f] denv[j][f] at [h][g][j]
             F2 dnew[K][K];       // [h][c]
 #pragma unroll
             for (int c = 0; c < K; ++c)
@@ -580,12 +581,9 @@ tnq_chain_train2_kernel(const __grid_constant__ ChainArgs a, long long B, const 
 #pragma unroll
                 for (int g = 0; g < K; ++g) {
 #pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        F2 t{0.f, 0.f};
+                    for (int j = 0; j < K; ++j) {   // both roles add into dLs[.][.][.]: one reduction for the two
 #pragma unroll
-                        for (int f = 0; f < K; ++f) t = fma2(T2[g][f], denv[j][f], t);
-                        const float sred = warp_sum(t.lo + t.hi);
-                        if (lane == 0) gq[(h * K + g) * K + j] += sred;
+                        for (int f = 0; f < K; ++f) accL[h][g][j] = fma2(T2[g][f], denv[j][f], accL[h][g][j]);
                     }
 #pragma unroll
                     for (int f = 0; f < K; ++f) {
