@@ -478,6 +478,7 @@ tnq_chain_train2_kernel(const __grid_constant__ ChainArgs a, long long B, const 
     float* slab = sm + (n - 1) * K3 + warp * SLAB;
     float* wacc = sm + (n - 1) * K3 + warps * SLAB;   // [warps][(n-1) * K3 + 1]
     const int acc_stride = (n - 1) * K3 + 1;
+    float* rscr = wacc + warps * acc_stride + warp * (K3 * 33);   // per-warp lane-reduction scratch [K3][33]
     for (int i = threadIdx.x; i < (n - 1) * K3; i += blockDim.x) {
         const int q = i / K3, r = i % K3, c = r / (K * K), e = (r / K) % K, f = r % K;
         float s = 0.f;
@@ -611,15 +612,28 @@ tnq_chain_train2_kernel(const __grid_constant__ ChainArgs a, long long B, const 
                         }
                     }
             }
+            // lane reduction through shared memory: [K3][33] transposed, lane v sums row v in lane order
+            // (3 shared-memory instructions per entry instead of a 5-step shuffle tree)
 #pragma unroll
             for (int c = 0; c < K; ++c)
 #pragma unroll
                 for (int e = 0; e < K; ++e)
 #pragma unroll
-                    for (int f = 0; f < K; ++f) {
-                        const float sred = warp_sum(accL[c][e][f].lo + accL[c][e][f].hi);
-                        if (lane == 0) gq[(c * K + e) * K + f] += sred;
-                    }
+                    for (int f = 0; f < K; ++f)
+                        rscr[((c * K + e) * K + f) * 33 + lane] = accL[c][e][f].lo + accL[c][e][f].hi;
+            __syncwarp();
+            if (lane < K3) {
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+                for (int l = 0; l < 32; l += 4) {
+                    p0 += rscr[lane * 33 + l];
+                    p1 += rscr[lane * 33 + l + 1];
+                    p2 += rscr[lane * 33 + l + 2];
+                    p3 += rscr[lane * 33 + l + 3];
+                }
+                gq[lane] += (p0 + p1) + (p2 + p3);
+            }
+            __syncwarp();
 #pragma unroll
             for (int h = 0; h < K; ++h)
 #pragma unroll
@@ -688,7 +702,7 @@ int launch_chain(const ChainArgs& a, long long B, int mode, const float* seed, f
     if constexpr (K <= 3) {
         if (mode != 0 && packed) {   // two samples per thread, packed FFMA2 (forward tape + reverse sweep)
             const size_t smem2 = sizeof(float) * ((size_t)(a.n - 1) * K3 + (size_t)warps * 64 * ((K * K) | 1) +
-                                                  (size_t)warps * acc_stride);
+                                                  (size_t)warps * acc_stride + (size_t)warps * K3 * 33);
             long long want2 = (B + 2 * CHAIN_THREADS - 1) / (2 * CHAIN_THREADS);
             const int grid2 = (int)(want2 < 1 ? 1 : (want2 > cap ? cap : want2));   // same bound as the workspace
             if (mode == 1) {
