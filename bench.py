@@ -6,9 +6,10 @@
 Prints ONE JSON line (rank 0).  Metric (BASELINE.json): samples/sec for the QCTN
 forward+backward contraction.  Workloads:
 
-  cfg3 (default)  training step (forward + loss + reverse sweep, + NCCL gradient all-reduce
-                  when N > 1) of the 24-qubit two-layer merged MPS network, K=3, float32,
-                  GLOBAL batch 16384 split over the N GPUs (strong scaling)
+  cfg3 (default)  training step (forward + loss + reverse sweep: the warp-level ladder kernel,
+                  replayed from a CUDA graph; + one gradient/loss exchange when N > 1: this
+                  repository's one-shot NVLink all-reduce kernel) of the 24-qubit two-layer merged
+                  MPS network, K=3, float32, GLOBAL batch 16384 split over the N GPUs (strong scaling)
   cfg2            forward probabilities, 16-qubit MPS, K=3, batch 4096
   cfg2-large      the same with batch 2^20 (bandwidth/compute visible above launch latency)
 
@@ -19,8 +20,9 @@ e_{K-1}; Mx = TNTensor-normalised Hermite-function outer products).
 `value`  : device-resident inputs, CUDA-event timed per step on the launching stream, L2
            flushed between timed steps, max over ranks.
 `e2e`    : the same step through the public engine API with the batch's measurement
-           matrices in PINNED HOST memory: host->device copy and the device->host read of the
-           loss are inside the timed region.
+           matrices in PINNED HOST memory: every timed step contains the host->device copy of one
+           batch (issued on a copy stream one step ahead, awaited inside the step) and the
+           device->host read of the loss.
 `--impl reference`: the reference's own CPU algorithm (oracle port of GreedyStrategy +
            torch.autograd, bit-identical to /root/reference on CPU, see oracle/) on the box's host
            cores, on a bounded sample of the same workload.
