@@ -178,8 +178,12 @@ int tnq_sgdg_step_flat(float* params, const float* grads, float* velocity, const
  *                   buffer has tnq_allreduce_oneshot_words(nmax) zero-initialised 32-bit words
  *   out[0, na+nb) = scale * sum over ranks of (src_a[0,na) ++ src_b[0,nb)), summed in rank order on
  *   every rank (bit-identical results).  All ranks must call it the same number of times.
+ * A peer that does not arrive within the timeout (default 600 000 ms; tnq_allreduce_set_timeout_ms) does
+ * not kill the context: out[] is filled with NaN, word 33 of this rank's symmetric buffer receives the
+ * epoch of the failed call and word 34 the first missing rank; the caller raises or falls back to NCCL.
  */
 int64_t tnq_allreduce_oneshot_words(int64_t nmax);
+int tnq_allreduce_set_timeout_ms(int64_t ms);
 int tnq_allreduce_oneshot(const uint64_t* peer_bufs_dev, int rank, int world, int64_t nmax, const float* src_a,
                           int64_t na, const float* src_b, int64_t nb, float* out, float scale, void* stream);
 

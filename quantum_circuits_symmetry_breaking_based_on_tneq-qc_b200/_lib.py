@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libtneq_b200.so")
 EXPORTS = ["tnq_device_check", "tnq_plan_create", "tnq_plan_destroy", "tnq_plan_num_inputs",
            "tnq_plan_num_outputs", "tnq_plan_query", "tnq_plan_run", "tnq_gemm_tf32x3", "tnq_permute_f32", "tnq_cplx_expand_f32",
            "tnq_cplx_fold_f32", "tnq_mps_chain", "tnq_mps_chain_workspace_bytes", "tnq_mps_ladder",
-           "tnq_mps_ladder_workspace_bytes", "tnq_allreduce_oneshot", "tnq_allreduce_oneshot_words", "tnq_sgdg_step", "tnq_sgdg_step_flat", "tnq_launch_count",
+           "tnq_mps_ladder_workspace_bytes", "tnq_allreduce_oneshot", "tnq_allreduce_oneshot_words", "tnq_allreduce_set_timeout_ms", "tnq_sgdg_step", "tnq_sgdg_step_flat", "tnq_launch_count",
            "tnq_last_error"]
 
 
@@ -66,6 +66,7 @@ def load():
                                    POINTER(c_void_p), c_double, c_void_p, c_int64, c_void_p]
     lib.tnq_allreduce_oneshot_words.argtypes = [c_int64]
     lib.tnq_allreduce_oneshot_words.restype = c_int64
+    lib.tnq_allreduce_set_timeout_ms.argtypes = [c_int64]
     lib.tnq_allreduce_oneshot.argtypes = [c_void_p, c_int, c_int, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                           c_float, c_void_p]
     lib.tnq_sgdg_step_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,

@@ -529,6 +529,8 @@ class B200Strategy(ContractionStrategy):
                   "replays": 0, "captures": 0, "max_captures": 8}
 
         def _raw_ptrs(cores_dict, circuit_states, measure_matrices):
+            """Identity of the operand buffers: address, dtype, shape and strides of every operand
+            (a graph bakes all of them in)."""
             T = torch.Tensor
             ptrs, tnts = [], []
             for k in core_names:
@@ -536,12 +538,12 @@ class B200Strategy(ContractionStrategy):
                 if not isinstance(v, T):
                     tnts.append((("core", k), v))
                     v = v.tensor
-                ptrs.append(v.data_ptr())
+                ptrs.append((v.data_ptr(), v.dtype, v.shape, v.stride()))
             for q, v in _items(circuit_states, nq).items():
                 if not isinstance(v, T):
                     tnts.append((("state", q), v))
                     v = v.tensor
-                ptrs.append(v.data_ptr())
+                ptrs.append((v.data_ptr(), v.dtype, v.shape, v.stride()))
             for q, v in _items(measure_matrices, nq).items():
                 if v is None:
                     ptrs.append(0)
@@ -549,9 +551,24 @@ class B200Strategy(ContractionStrategy):
                 if not isinstance(v, T):
                     tnts.append((("mx", q), v))
                     v = v.tensor
-                ptrs.append(v.data_ptr())
-                ptrs.append(v.shape[0])
+                ptrs.append((v.data_ptr(), v.dtype, v.shape, v.stride()))
             return tuple(ptrs), tnts
+
+        def _captures_callers_buffers(key, call, cores):
+            """True when the launches would read exactly the caller's buffers: prepare() converted
+            nothing (device, dtype) and the route will not make contiguous copies.  Otherwise the
+            graph would bake in the addresses of temporaries that are freed after the capture."""
+            seen = {e[0] for e in key if e != 0}
+            for t in list(cores) + list(call.states.values()) + list(call.mxs.values()):
+                if t.data_ptr() not in seen:
+                    return False
+            if any(not c.is_contiguous() for c in cores) or any(not t.is_contiguous() for t in call.states.values()):
+                return False
+            for m in call.mxs.values():
+                st = m.stride()
+                if st[-1] != 1 or st[-2] != m.shape[-1]:
+                    return False
+            return True
 
         def _scale_of(bound, tnt):
             if not tnt:
@@ -592,7 +609,8 @@ class B200Strategy(ContractionStrategy):
                     return loss, grads, values, scale
                 if graphs["seen"].get(key) and graphs["captures"] < graphs["max_captures"]:
                     call, cores, scale = prepare(cores_dict, circuit_states, measure_matrices, right_cores_dict)
-                    if call.graphable() and all(not c.requires_grad or c.is_leaf for c in cores):
+                    if call.graphable() and all(not c.requires_grad or c.is_leaf for c in cores) \
+                            and _captures_callers_buffers(key, call, cores):
                         dev = cores[0].device
                         torch.cuda.synchronize(dev)
                         graph = torch.cuda.CUDAGraph()

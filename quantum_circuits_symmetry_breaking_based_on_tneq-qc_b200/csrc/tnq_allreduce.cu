@@ -15,8 +15,14 @@
 // has published e+1, i.e. after every peer finished reading epoch e.  The epoch counter lives in
 // device memory, so the launch can be replayed from a CUDA graph.
 //
-// Symmetric buffer layout (32-bit words): [0,32) flags[2][16] | [32] epoch | [64, 64+NMAX) slot 0 |
-// [64+NMAX, 64+2 NMAX) slot 1.
+// A peer that does not show up within the timeout (default 10 minutes, tnq_allreduce_set_timeout_ms;
+// NCCL's default is of the same order) does NOT trap the context: the kernel records the epoch and
+// the missing rank in the error words of its own buffer, fills the output with NaN (so the loss the
+// host reads next is NaN and cannot be mistaken for a result) and returns; the host turns that into
+// an exception (distributed/oneshot.py: check()) or falls back to NCCL.
+//
+// Symmetric buffer layout (32-bit words): [0,32) flags[2][16] | [32] epoch | [33] error epoch (0 = none) |
+// [34] first missing rank | [64, 64+NMAX) slot 0 | [64+NMAX, 64+2 NMAX) slot 1.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -48,13 +54,25 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+long long g_timeout_ns = 600LL * 1000 * 1000 * 1000;
+
 __global__ void __launch_bounds__(AR_THREADS)
 tnq_allreduce_oneshot_kernel(const uint64_t* __restrict__ peers, int rank, int world, long long nmax,
                              const float* __restrict__ src_a, long long na, const float* __restrict__ src_b,
-                             long long nb, float* __restrict__ out, float scale) {
+                             long long nb, float* __restrict__ out, float scale, long long timeout_ns) {
     __shared__ uint32_t epoch_s;
+    __shared__ int missing_s;
     uint32_t* own = reinterpret_cast<uint32_t*>(peers[rank]);
-    if (threadIdx.x == 0) epoch_s = own[32] + 1u;
+    if (threadIdx.x == 0) {
+        epoch_s = own[32] + 1u;
+        missing_s = -1;
+    }
     __syncthreads();
     const uint32_t e = epoch_s, par = e & 1u;
     const long long n = na + nb;
@@ -65,12 +83,25 @@ tnq_allreduce_oneshot_kernel(const uint64_t* __restrict__ peers, int rank, int w
     if ((int)threadIdx.x < world) {
         uint32_t* peer = reinterpret_cast<uint32_t*>(peers[threadIdx.x]);
         st_release_sys(peer + par * AR_MAX_WORLD + rank, e);
-        const long long t0 = clock64();
+        const unsigned long long t0 = global_ns();
+        unsigned spins = 0;
         while (ld_acquire_sys(own + par * AR_MAX_WORLD + threadIdx.x) != e) {
-            if (clock64() - t0 > 8000000000LL) __trap();     // a missing peer surfaces as an error, not a hang
+            if ((++spins & 1023u) == 0 && global_ns() - t0 > (unsigned long long)timeout_ns) {
+                atomicMax(&missing_s, (int)threadIdx.x);     // a missing peer surfaces as an error, not a hang
+                break;
+            }
         }
     }
     __syncthreads();
+    if (missing_s >= 0) {                                    // no result is published
+        for (long long i = threadIdx.x; i < n; i += AR_THREADS) out[i] = __int_as_float(0x7fc00000);
+        if (threadIdx.x == 0) {
+            own[33] = e;
+            own[34] = (uint32_t)missing_s;
+            own[32] = e;
+        }
+        return;
+    }
     for (long long i = threadIdx.x; i < n; i += AR_THREADS) {
         float s = 0.f;
         for (int r = 0; r < world; ++r)
@@ -86,6 +117,12 @@ extern "C" {
 
 int64_t tnq_allreduce_oneshot_words(int64_t nmax) { return AR_HEADER + 2 * nmax; }
 
+int tnq_allreduce_set_timeout_ms(int64_t ms) {
+    if (ms <= 0) return tnq_internal_fail("tnq_allreduce_set_timeout_ms: the timeout must be positive");
+    g_timeout_ns = ms * 1000000LL;
+    return 0;
+}
+
 int tnq_allreduce_oneshot(const uint64_t* peer_bufs_dev, int rank, int world, int64_t nmax, const float* src_a,
                           int64_t na, const float* src_b, int64_t nb, float* out, float scale, void* stream) {
     if (!peer_bufs_dev || !src_a || !out || world < 1 || world > AR_MAX_WORLD || rank < 0 || rank >= world)
@@ -93,7 +130,7 @@ int tnq_allreduce_oneshot(const uint64_t* peer_bufs_dev, int rank, int world, in
     if (na < 0 || nb < 0 || na + nb > nmax || (nb > 0 && !src_b))
         return tnq_internal_fail("tnq_allreduce_oneshot: message does not fit the symmetric buffer");
     tnq_allreduce_oneshot_kernel<<<1, AR_THREADS, 0, (cudaStream_t)stream>>>(peer_bufs_dev, rank, world, nmax, src_a, na,
-                                                                              src_b, nb, out, scale);
+                                                                              src_b, nb, out, scale, g_timeout_ns);
     tnq_internal_count_launch();
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_allreduce_oneshot launch");

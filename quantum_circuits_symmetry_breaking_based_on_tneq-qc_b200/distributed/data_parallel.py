@@ -15,8 +15,9 @@ with the deviations the SURVEY lists as necessary:
   * gradients AND the loss travel in ONE packed NCCL all-reduce per step (NVLink/NVSwitch);
     the reference issues one blocking collective per core plus one for the loss
     (comm_torch.py:510-522) and calls a method that does not exist (defect D9);
-  * the SGDG step draws `random.randint` for its 1 % QR retraction
-    (backend_pytorch.py:382): ranks are seeded identically so the replicas stay in lock step.
+  * the SGDG step draws `random.randint` for its 1 % QR retraction (backend_pytorch.py:382): every
+    trainer owns a dedicated `random.Random(config.seed)` that the optimizer state carries ('rng'),
+    so the replicas stay in lock step whatever else in the process uses the `random` module.
 """
 from __future__ import annotations
 
@@ -76,7 +77,8 @@ class DataParallelTrainer:
         self.accumulated_grads: Optional[List[torch.Tensor]] = None
         self.accumulation_count = 0
         self._oneshot, self._oneshot_tried = None, False
-        random.seed(self.config.seed)          # lock-step QR retractions on every rank
+        # lock-step QR retractions on every rank: a private stream, not the process-global one
+        self.optimizer.opt_state["rng"] = random.Random(self.config.seed)
 
     def _log(self, msg: str, level: str = "info"):
         if self.comm.is_main_process():
@@ -93,11 +95,19 @@ class DataParallelTrainer:
 
     def sync_model_weights(self, src: int = 0):
         """Make every replica start from rank `src`'s cores (one packed broadcast)."""
-        raws = []
+        raws, tnts = [], []
         for name in self.qctn.cores:
             w = self.qctn.cores_weights[name]
-            raws.append(w.tensor if hasattr(w, "scale") and hasattr(w, "tensor") else w)
+            if hasattr(w, "scale") and hasattr(w, "tensor"):
+                raws.append(w.tensor)
+                tnts.append(w)
+            else:
+                raws.append(w)
         self.comm.broadcast_tensors_packed(raws, src=src)
+        if tnts:                                   # TNTensor cores: the host-side scales travel too
+            scales = self.comm.broadcast_object([(float(w.scale), float(w.log_scale)) for w in tnts], src=src)
+            for w, (sc, ls) in zip(tnts, scales):
+                w.scale, w.log_scale = sc, ls
 
     # ---- one step ---------------------------------------------------------------------
     def compute_local_gradients(self, data: Dict, circuit_states_list: List) -> Tuple[torch.Tensor, List[torch.Tensor]]:
@@ -171,6 +181,8 @@ class DataParallelTrainer:
             g, loss_avg = self.sync_gradients_and_loss(grads, loss)
             self.optimizer.step(self.qctn, g)
             loss_avg = float(loss_avg)
+            if loss_avg != loss_avg and self._oneshot is not None:
+                self._oneshot.check()              # NaN: did the exchange give up on a missing peer?
         self.optimizer.iter += 1
         return loss_avg
 

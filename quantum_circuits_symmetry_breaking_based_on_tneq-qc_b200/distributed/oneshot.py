@@ -19,10 +19,30 @@ import torch.distributed as dist
 from .. import _lib
 
 
+class OneShotTimeout(RuntimeError):
+    """A peer did not reach the exchange within the timeout (tnq_allreduce_set_timeout_ms)."""
+
+
+def _precheck(device: torch.device) -> bool:
+    """Everything that can fail WITHOUT a collective, so that ranks agree before the first one."""
+    try:
+        import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+        _lib.load()
+        if device.type != "cuda":
+            return False
+        me = device.index if device.index is not None else torch.cuda.current_device()
+        return all(p == me or torch.cuda.can_device_access_peer(me, p) for p in range(torch.cuda.device_count()))
+    except Exception:  # noqa: BLE001
+        return False
+
+
 class OneShotAllReduce:
     def __init__(self, nmax: int, device: torch.device, group=None):
+        import os
         import torch.distributed._symmetric_memory as symm_mem
         self.lib = _lib.load()
+        if os.environ.get("TNQ_ONESHOT_TIMEOUT_S"):
+            _lib.check(self.lib.tnq_allreduce_set_timeout_ms(int(float(os.environ["TNQ_ONESHOT_TIMEOUT_S"]) * 1000)))
         self.nmax, self.device = int(nmax), device
         group = group if group is not None else dist.group.WORLD
         words = int(self.lib.tnq_allreduce_oneshot_words(self.nmax))
@@ -40,7 +60,12 @@ class OneShotAllReduce:
             return None
         if dist.get_backend() != "nccl":
             return None
-        ok = torch.ones(1, device=device)
+        # ranks first agree on what each can check locally (library, symmetric-memory module, peer
+        # access): a rank that cannot take part must not leave its peers inside the rendezvous
+        ok = torch.tensor([1.0 if _precheck(device) else 0.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() <= 0:
+            return None
         try:
             obj = cls(nmax, device, group)
         except Exception as exc:  # noqa: BLE001 -- any set-up failure means "use NCCL"
@@ -63,3 +88,13 @@ class OneShotAllReduce:
                                                       extra.data_ptr() if extra is not None else None, nb, out.data_ptr(),
                                                       1.0 / self.world, torch.cuda.current_stream(self.device).cuda_stream))
         return out
+
+    def check(self) -> None:
+        """Raise OneShotTimeout if any exchange so far gave up waiting for a peer (its output was NaN).
+        Synchronises the stream; callers use it when a loss comes back NaN, not on the hot path."""
+        torch.cuda.synchronize(self.device)
+        words = self.buf.view(torch.int32)[32:35].tolist()
+        if words[1] != 0:
+            self.buf.view(torch.int32)[33:35].zero_()      # reported once
+            raise OneShotTimeout(f"one-shot all-reduce: rank {words[2]} did not arrive in epoch {words[1]} "
+                                 f"(rank {self.rank} of {self.world})")

@@ -1,7 +1,8 @@
 """Parameter updates (reference: tneq_qc/backends/backend_pytorch.py:200-468).
 
 optimizer_update(params, grads, state, method, hyperparams) -> (new_params, state)
-with methods adam | sgd | momentum | nesterov | rmsprop | sgdg.  'sgdg' is the
+with methods adam | sgd | momentum | nesterov | rmsprop | sgdg.  state['rng'] (optional, a
+random.Random) replaces the process-global `random` stream for SGDG's 1 % QR-retraction draws.  'sgdg' is the
 Stiefel-manifold SGD with a Cayley retraction used by the examples
 (examples/example_train_single_node.py:229-240).  Params may be TNTensors:
 the update acts on tensor*scale with grad/scale and re-wraps (:205-266).
@@ -160,9 +161,10 @@ def _sgdg_flat_step(params, grads, state, lr, mom, out):
             state["_flat_poff"] = [int(x) for x in p_off]
         flat = torch.cat([p.reshape(-1) for p in params])
         p_off = state["_flat_poff"]
+        rng = state.get("rng", random)
         for n in range(len(params)):
             # the reference draws one random number per Stiefel core (backend_pytorch.py:382)
-            if random.randint(1, 101) == 1:
+            if rng.randint(1, 101) == 1:
                 r, c = shapes[n]
                 x = flat[p_off[n]: p_off[n] + sizes[n]].view(r, c)
                 x.copy_(_qr_retract(x / (torch.norm(x, p=2, dim=1, keepdim=True) + 1e-8)))
@@ -186,9 +188,10 @@ def _sgdg_kernel_step(idx, params, grads, state, lr, mom, out):
         # the update is in place on the device, the reference returns fresh tensors: work on a packed copy
         flat = torch.cat([params[i].reshape(-1) for i in idx])
         gs = [grads[i].contiguous() for i in idx]
+        rng = state.get("rng", random)
         for n, i in enumerate(idx):
             # the reference draws one random number per Stiefel core (backend_pytorch.py:382)
-            if random.randint(1, 101) == 1:
+            if rng.randint(1, 101) == 1:
                 r, c = shapes[n]
                 off = sum(sizes[:n])
                 x = flat[off: off + sizes[n]].view(r, c)
@@ -251,7 +254,7 @@ def _sgdg(params, grads, state, hp):
         if not (stiefel and unity.shape[0] <= unity.shape[1]):
             out[i] = p - lr * g
             continue
-        if random.randint(1, 101) == 1:  # occasional QR retraction, same RNG stream as the reference
+        if state.get("rng", random).randint(1, 101) == 1:  # occasional QR retraction, same RNG stream as the reference
             unity = _qr_retract(unity)
         if state["momentum_buffer"][i] is None:
             state["momentum_buffer"][i] = torch.zeros(gx.T.shape, dtype=gx.dtype, device=p.device)
@@ -266,5 +269,10 @@ def _sgdg(params, grads, state, hp):
         y = torch.inverse(eye - (alpha / 2) * w) @ (eye + (alpha / 2) * w) @ hconj(unity)
         pn = hconj(y)
         out[i] = pn.reshape(shp) if len(shp) > 2 else pn
-        state["momentum_buffer"][i] = w @ hconj(unity)
+        new_v = w @ hconj(unity)
+        old_v = state["momentum_buffer"][i]
+        if old_v.shape == new_v.shape and old_v.dtype == new_v.dtype:
+            old_v.copy_(new_v)        # keep the buffer (it may be a view of the flat momentum buffer of tnq_sgdg_step_flat)
+        else:
+            state["momentum_buffer"][i] = new_v
     return out, state

@@ -1,7 +1,8 @@
-"""The one-shot NVLink all-reduce kernel (csrc/tnq_allreduce.cu) against NCCL, on two GPUs.
+"""The one-shot NVLink all-reduce kernel (csrc/tnq_allreduce.cu) against NCCL, on every visible GPU
+(two or more), and its behaviour when a peer is late.
 
-Needs two visible GPUs (the round-end GPU tier has one: skipped there; run with
-`gpurun --gpus 2 -- python -m pytest tests/test_gpu_oneshot.py -m gpu`)."""
+Needs at least two visible GPUs (the round-end GPU tier has one: skipped there; run with
+`gpurun --gpus 2 -- python -m pytest tests/test_gpu_oneshot.py -m gpu`, logs kept in profiles/)."""
 import os
 import subprocess
 import sys
@@ -38,6 +39,34 @@ for it in range(50):                       # many epochs: exercises the double-b
     gathered = [torch.empty_like(got) for _ in range(dist.get_world_size())]
     dist.all_gather(gathered, got)
     assert all(torch.equal(g, gathered[0]) for g in gathered)      # bit-identical on all ranks
+# a late peer: rank 1 arrives after the timeout.  The early ranks get NaN + OneShotTimeout (no trap,
+# the context survives), the late rank completes with everyone's data, and the next exchange is
+# back in step on all ranks.
+import time
+from tneq_b200.distributed.oneshot import OneShotTimeout
+from tneq_b200 import _lib
+_lib.check(_lib.load().tnq_allreduce_set_timeout_ms(300))
+dist.barrier(); torch.cuda.synchronize()
+flat = torch.full((n,), float(rank + 1), device=dev)
+if rank == 1:
+    time.sleep(2.0)
+got = red.mean(flat, None)
+torch.cuda.synchronize()
+if rank == 1:
+    assert torch.isfinite(got).all() and abs(got[0].item() - (dist.get_world_size() + 1) / 2) < 1e-6
+    red.check()
+else:
+    assert torch.isnan(got).all(), "an exchange that gave up must not publish numbers"
+    try:
+        red.check()
+        raise AssertionError("check() did not raise")
+    except OneShotTimeout as exc:
+        assert "rank 1" in str(exc)
+_lib.check(_lib.load().tnq_allreduce_set_timeout_ms(600000))
+dist.barrier()
+got = red.mean(flat, None)
+torch.cuda.synchronize()
+assert abs(got[5].item() - (dist.get_world_size() + 1) / 2) < 1e-6
 dist.barrier()
 dist.destroy_process_group()
 print("ONESHOT-OK", rank)
@@ -50,8 +79,9 @@ def test_oneshot_allreduce_matches_nccl(built_lib, tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, TNQ_ROOT=ROOT)
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    world = min(torch.cuda.device_count(), 8)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("ONESHOT-OK") == 2
+    assert out.stdout.count("ONESHOT-OK") == world

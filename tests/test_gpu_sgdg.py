@@ -126,6 +126,29 @@ def test_sgdg_kernel_qr_retraction_and_tntensor(built_lib):
         assert (val - b).norm() / b.norm() < TOL
 
 
+def test_sgdg_kernel_matches_reference_fixture(built_lib):
+    """tnq_sgdg_step against three consecutive steps of the REAL reference (tests/golden/sgdg_f32*.npz,
+    written by oracle/make_golden.py from backend_pytorch.py:349-468), momentum 0 and 0.9, including a
+    step where the reference's 1 % QR retraction fires."""
+    import glob
+    import os
+    from test_oracle_golden import load_sgdg
+    from tneq_b200.optim import steps as opt_steps
+    dev = torch.device("cuda:0")
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "sgdg_f32*.npz"))):
+        params, grads, want, lr, momentum, seed, dtype = load_sgdg(path)
+        params = [p.to(dev) for p in params]
+        state = {}
+        random.seed(seed)
+        for k in range(3):
+            params, state = opt_steps.optimizer_update(list(params), [g.to(dev) for g in grads[k]], state, "sgdg",
+                                                       dict(learning_rate=lr, momentum=momentum, stiefel=True))
+            params = [p.detach() for p in params]
+            for a, b in zip(params, want[k]):
+                err = (a.cpu().double() - b.double()).norm() / b.double().norm()
+                assert err < (k + 1) * TOL, (os.path.basename(path), k, err)
+
+
 def test_sgdg_bad_arguments(built_lib):
     from tneq_b200 import _lib
     lib = _lib.load()

@@ -15,7 +15,8 @@ import torch
 from oracle import qctn_oracle as oc
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-FILES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+FILES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(f).startswith("sgdg_"))
+SGDG_FILES = sorted(glob.glob(os.path.join(GOLDEN, "sgdg_*.npz")))
 
 
 def load_case(path):
@@ -98,3 +99,28 @@ def test_known_answers():
         vals.append(float(oc.loss_and_grads(graph, pert, states, mx)[0]))
     fd = (vals[0] - vals[1]) / (2 * h)
     assert abs(fd - float(grads[1][idx])) < 1e-6 * max(1.0, abs(fd))
+
+
+def load_sgdg(path):
+    z = np.load(path)
+    n = len([k for k in z.files if k.startswith("param_")])
+    params = [torch.from_numpy(z[f"param_{i}"]) for i in range(n)]
+    grads = [[torch.from_numpy(z[f"grad_{k}_{i}"]) for i in range(n)] for k in range(3)]
+    steps = [[torch.from_numpy(z[f"step_{k}_{i}"]) for i in range(n)] for k in range(3)]
+    return params, grads, steps, float(z["lr"]), float(z["momentum"]), int(z["rng_seed"]), str(z["dtype"])
+
+
+@pytest.mark.parametrize("path", SGDG_FILES, ids=[os.path.basename(f)[:-4] for f in SGDG_FILES])
+def test_oracle_sgdg_reproduces_reference_steps(path):
+    """oc.sgdg_step against three consecutive steps of the REAL reference's optimizer_update('sgdg')
+    (backend_pytorch.py:200-268, 349-468; fixtures written by oracle/make_golden.py, which asserts
+    bit-identity in the build container).  The Python-random seed fires the 1 % QR retraction."""
+    import random
+    params, grads, steps, lr, momentum, seed, dtype = load_sgdg(path)
+    rt = 1e-5 if dtype == "float32" else 1e-12
+    rng = random.Random(seed)
+    state = {}
+    for k in range(3):
+        params, state = oc.sgdg_step(params, grads[k], state, lr=lr, momentum=momentum, stiefel=True, rng=rng)
+        for a, b in zip(params, steps[k]):
+            assert a.shape == b.shape and (a - b).abs().max() <= rt * b.abs().max()

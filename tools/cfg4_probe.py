@@ -1,4 +1,4 @@
-import sys, time, ctypes; sys.path.insert(0,'/root/repo')
+import sys, time, ctypes; sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch, tneq_b200
 from tneq_b200 import _lib
 lib = _lib.load()

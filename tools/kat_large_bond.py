@@ -1,4 +1,4 @@
-import sys; sys.path.insert(0,'/root/repo')
+import sys; sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch, tneq_b200
 H = tneq_b200.QCTNHelper
 for K, n in [(8,6),(16,6),(32,4),(32,6),(64,4)]:
