@@ -1,7 +1,8 @@
 """Import the REAL reference (`/root/reference/tneq_qc`) in the build container.
 
-TEST INFRASTRUCTURE ONLY, and only usable where /root/reference exists (it does
-not exist on the GPU box).  Used by `oracle/make_golden.py` to (1) prove the
+TEST INFRASTRUCTURE ONLY.  The reference is imported from /root/reference in the build
+container and, on the GPU box (where that path does not exist), from the unmodified copy that
+`__graft_entry__.build()` stages under the git-ignored baseline/_ref/ (`stage()` below).  Used by `oracle/make_golden.py` to (1) prove the
 restatement in `qctn_oracle.py` bit-identical to the reference on CPU and
 (2) generate the fixtures committed under tests/golden/.
 
@@ -21,8 +22,27 @@ import sys
 
 import torch  # noqa: F401  (must be imported before the shim is visible)
 
-REF_ROOT = os.environ.get("TNEQ_REFERENCE_ROOT", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_opt_einsum_shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# where the reference package lives: the read-only checkout in the build container, else the
+# git-ignored copy that build() stages under baseline/_ref/ so that it travels to the GPU box
+STAGED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+REF_ROOT = os.environ.get("TNEQ_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/tneq_qc") else STAGED)
+_SHIM = os.path.join(_HERE, "_opt_einsum_shim")
+
+
+def stage(src: str = "/root/reference") -> bool:
+    """Copy the reference's Python package (unmodified) into baseline/_ref/ (git-ignored, not part of
+    this repository's history; it only rides along to the GPU box).  Returns False where the
+    reference checkout does not exist."""
+    import shutil
+    pkg = os.path.join(src, "tneq_qc")
+    if not os.path.isdir(pkg):
+        return False
+    dst = os.path.join(STAGED, "tneq_qc")
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    shutil.copytree(pkg, dst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc", "*.so", "*.safetensors", "*.npz"))
+    return True
 
 
 def available() -> bool:

@@ -109,6 +109,21 @@ class _Bound:
             self._scale_prog = prog
         return self._scale_prog
 
+    def ones(self, elems: int, real_dtype) -> torch.Tensor:
+        """A vector of ones in the plan's real representation (complex: interleaved (1, 0) pairs): the
+        partner of an edge that einsum sums over on its own (cgraph.build_forward)."""
+        dt = {"f32": torch.float32, "f64": torch.float64}.get(real_dtype, real_dtype)
+        key = (int(elems), dt)
+        cache = self.__dict__.setdefault("_ones", {})
+        if key not in cache:
+            if self.plan.complex_mode:
+                t = torch.zeros(elems // 2, 2, dtype=dt, device=self.device)
+                t[:, 0] = 1.0
+                cache[key] = t.reshape(-1)
+            else:
+                cache[key] = torch.ones(elems, dtype=dt, device=self.device)
+        return cache[key]
+
     def gemm_runner(self, mode: str):
         from .gemm_path import GemmPathRunner
         if mode not in self._gemm:
@@ -155,6 +170,8 @@ class _Call:
                 out.append((t, 0, 0))
             elif kind == "state":
                 out.append((_real_view(self.states[key].detach().contiguous()), 0, 0))
+            elif kind == "ones":                 # partner of an edge that einsum sums over on its own
+                out.append((self.bound.ones(slot.elems, prog.real_dtype), 0, 0))
             elif kind == "mx":
                 m = self.mxs[key].detach()
                 inner = m.shape[-2] * m.shape[-1]
@@ -291,6 +308,10 @@ class _Call:
             out[key] = _real_view(c.detach().contiguous())
         for q, s_ in self.states.items():
             out[("state", q)] = _real_view(s_.detach().contiguous())
+        g = self.bound.gemm_runner("fwd").g
+        for key, ids in g.inputs.items():
+            if key[0] == "ones":
+                out[key] = self.bound.ones(g.size(g.nodes[ids[0]].idx), torch.float32)
         for q, m in self.mxs.items():
             m = m.detach()
             if m.shape[0] == 1 and self.B != 1:
@@ -392,8 +413,16 @@ class _Call:
 class B200Strategy(ContractionStrategy):
     """Whole-sweep CUDA contraction; registered for modes 'balanced' and 'full'."""
 
+    # class of the TNTensor results; reference_plugin.register() substitutes the reference's own
+    # class so that the isinstance checks of its EngineSiamese (engine_siamese.py:332,476) hold
+    tntensor_cls = TNTensor
+
     def check_compatibility(self, qctn, shapes_info: Dict[str, Any]) -> bool:
-        return True
+        # Inside the reference (reference_plugin.register) this strategy shares the registry with
+        # GreedyStrategy: a network that lives on another backend (the reference's own 'pytorch' CPU
+        # backend) stays with the reference's strategies -- there is no CPU path here.
+        name = getattr(getattr(qctn, "backend", None), "get_backend_name", None)
+        return name is None or name() == "b200"
 
     def estimate_cost(self, qctn, shapes_info: Dict[str, Any]) -> float:
         # below GreedyStrategy's fixed 5e5 (greedy_strategy.py:602-608) so that
@@ -406,6 +435,7 @@ class B200Strategy(ContractionStrategy):
 
     def get_compute_function(self, qctn, shapes_info: Dict[str, Any], backend, right_qctn="symmetric") -> Callable:
         plans: Dict[Any, _Bound] = {}
+        tnt_cls = self.tntensor_cls
         nq = qctn.nqubits
         table = qctn.adjacency_table
         core_names = list(qctn.cores)
@@ -511,7 +541,7 @@ class B200Strategy(ContractionStrategy):
             else:
                 res = call.forward(cores)
             if scale is not None:
-                return TNTensor(res, scale=scale[0], log_scale=scale[1])
+                return tnt_cls(res, scale=scale[0], log_scale=scale[1])
             return res
 
         # ---- CUDA-graph replay of the fused training step (opt-in) ---------------------------------

@@ -351,9 +351,18 @@ def build_forward(schedule: GreedySchedule, complex_mode: bool, core_shapes: Dic
                 alive[host] = g.contract(alive[host], nodes[k])
         live = [alive[k] for k in sorted(alive)]
         sets = [set(n.idx[:-1] if n.cplx else n.idx) for n in live]
-        for i in set().union(*sets):
+        # An edge that occurs in ONE operand and not in the output is summed over by einsum without a
+        # partner (the reference's wiring of `right_qctn=<QCTN>` leaves such edges,
+        # greedy_strategy.py:764-822): contract it with a vector of ones -- an input like a circuit state.
+        for i in sorted(set().union(*sets)):
             if sum(i in s for s in sets) == 1 and i not in out_ids:
-                raise NotImplementedError("an edge that is summed without a partner is not supported")
+                k = next(k for k, s in enumerate(sets) if i in s)
+                okey = (len(g.inputs), i)
+                ones = g.add_input(Operand("ones", okey), [i] + ([g.new_index(2)] if complex_mode else []),
+                                   batched=False, cplx=complex_mode)
+                g.inputs[("ones", okey)] = [ones.id]
+                live[k] = g.contract(live[k], ones)
+                sets[k] = set(live[k].idx[:-1] if live[k].cplx else live[k].idx)
         pool = list(live)
         for a, b in _pairwise_order(sets, [n.batched for n in live], set(out_ids), g.dims):
             pool.append(g.contract(pool[a], pool[b]))

@@ -28,8 +28,9 @@ def register(tneq_qc_module=None):
     from .backends.backend_b200 import B200Backend
     from .contractor.b200_strategy import B200Strategy
 
+    ref_tnt = importlib.import_module("tneq_qc.core.tn_tensor").TNTensor
     RefBackend = type("B200Backend", (B200Backend, bi.ComputeBackend), {})
-    RefStrategy = type("B200Strategy", (B200Strategy, cb.ContractionStrategy), {})
+    RefStrategy = type("B200Strategy", (B200Strategy, cb.ContractionStrategy), {"tntensor_cls": ref_tnt})
     bf.BackendFactory.register_backend("b200", RefBackend)
     cc.StrategyCompiler.register_strategy(RefStrategy(), modes=["balanced", "full"])
     return RefBackend, RefStrategy

@@ -184,6 +184,14 @@ def test_reference_plugin_registration():
     be, _ = rh.make_engine()
     with rh.quiet():
         q = ns.QCTN(ns.QCTNHelper.generate_example_graph(n=4, graph_type="mps", dim_char="2"), backend=be)
+        # a network that lives on the reference's CPU backend stays with the reference's strategies
+        fn, name, cost = ns.StrategyCompiler(mode="balanced").compile(q, {}, be, right_qctn="symmetric")
+        assert name == "greedy"
+
+        class OnB200:                      # (B200Backend itself cannot be constructed without a GPU)
+            def get_backend_name(self):
+                return "b200"
+        q.backend = OnB200()
         fn, name, cost = ns.StrategyCompiler(mode="balanced").compile(q, {}, be, right_qctn="symmetric")
     assert name == "b200" and cost < 5e5
     assert fn.equations(oc.unit_states(4, 2), [torch.randn(2, 2, 2)] * 4)[0] == "cdef,c,aeg,higj,h,d,i->ajf"

@@ -139,3 +139,77 @@ def test_disconnected_network_is_the_product_of_its_parts():
         psi = u[1, :] if False else states[q].numpy() @ u          # <s|U
         want = want * np.einsum("i,bij,j->b", psi, mxs[q].numpy(), psi)
     assert np.allclose(got, want, rtol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+def test_right_qctn_given_as_second_network(dtype):
+    """`right_qctn=<QCTN>` (engine_siamese.py:304,390; the 'qctn' branch of the greedy sweep): the
+    right-hand copy is a second set of cores, used as given (no conjugation, no transposition).
+    Values and the gradients of both core sets through the device program vs the oracle; where the
+    reference checkout exists, the oracle's numbers are first checked against the reference's own."""
+    from helpers import make_case, clone_mx
+    K, n, B = 2, 4, 6
+    graph = tneq_b200.QCTNHelper.generate_example_graph(n=n, graph_type="mps", dim_char=str(K))
+    names, table, nq, cores, states, mxs = make_case(graph, K, B, dtype, tnt=False)
+    torch.manual_seed(5)
+    rcores = {k: v + 0.2 * torch.randn_like(v) for k, v in cores.items()}
+    want = oc.greedy_contract(table, nq, cores, states, clone_mx(mxs), right="qctn", right_table=table, right_cores=rcores)
+    from oracle import ref_harness as rh
+    if rh.available():
+        import contextlib, io
+        ns = rh.load()
+        with contextlib.redirect_stdout(io.StringIO()):
+            be = ns.BackendFactory.create_backend("pytorch", device="cpu", dtype=dtype)
+            eng = ns.EngineSiamese(backend=be, strategy_mode="balanced", mx_K=K)
+            ql, qr = ns.QCTN(graph, backend=be), ns.QCTN(graph, backend=be)
+            for k in names:
+                ql.cores_weights[k], qr.cores_weights[k] = cores[k], rcores[k]
+            ref = eng.contract_with_compiled_strategy(ql, states, clone_mx(mxs), right_qctn=qr)
+        assert torch.equal(ref, oc.abs_square(want))
+    q = tneq_b200.QCTN(graph)
+    sd, mi = signature_of(q.nqubits, states, mxs)
+    shapes = {c: q.core_shape(c) for c in q.cores}
+    plan = ContractionPlan(q.adjacency_table, q.nqubits, shapes, sd, mi, dtype, right="qctn",
+                           right_table=q.adjacency_table, right_core_shapes=shapes)
+
+    slot_elems = {}
+
+    def marshal2(prog, gradseed=None):
+        ins = []
+        for s in prog.inputs:
+            slot_elems[s.key] = s.elems
+            kind, key = s.key
+            if kind == "rcore":
+                ins.append(to_real(rcores[key]).reshape(-1))
+            else:
+                ins.append(marshal_one(kind, key, gradseed))
+        return ins
+
+    def marshal_one(kind, key, gradseed):
+        if kind == "core":
+            return to_real(cores[key]).reshape(-1)
+        if kind == "state":
+            return to_real(states[key]).reshape(-1)
+        if kind == "mx":
+            return to_real(oc._raw(mxs[key])).reshape(B, -1)
+        if kind == "ones":
+            return to_real(torch.ones(slot_elems[(kind, key)] // (2 if plan.complex_mode else 1), dtype=cores[names[0]].dtype)).reshape(-1)
+        return gradseed
+
+    pf = plan.program("fwd")
+    got = em.run(pf.to_blob(), marshal2(pf), B, dtype=np.float64)[0]
+    assert np.abs(got - to_real(want).reshape(B, -1)).max() <= 1e-12 * np.abs(to_real(want)).max()
+    # gradients of both core sets: seed = d sum(value) / d result
+    cl = {k: v.clone().requires_grad_(True) for k, v in cores.items()}
+    cr = {k: v.clone().requires_grad_(True) for k, v in rcores.items()}
+    res = oc.greedy_contract(table, nq, cl, states, clone_mx(mxs), right="qctn", right_table=table, right_cores=cr)
+    resr = res.detach().clone().requires_grad_(True)
+    oc.abs_square(resr).sum().backward()
+    oc.abs_square(res).sum().backward()
+    pb = plan.program("bwd")
+    outs = em.run(pb.to_blob(), marshal2(pb, gradseed=to_real(resr.grad).reshape(B, -1)), B, dtype=np.float64)
+    for kind, src in (("core", cl), ("rcore", cr)):
+        for name in names:
+            gg = outs[pb.output_index(("grad", kind, name))].reshape(-1)
+            gw = to_real(src[name].grad).reshape(-1)
+            assert np.abs(gg - gw).max() <= 1e-10 * np.abs(gw).max() + 1e-300, (kind, name)
