@@ -148,7 +148,36 @@ def time_reference(args, wl):
     n_steps = args.steps if args.impl == "reference" else 3
     n_warm = max(1, args.warmup) if args.impl == "reference" else 1
 
+    # The REAL reference (unmodified tneq_qc: /root/reference in the build container, the copy staged by
+    # build() under baseline/_ref/ on the GPU box) through its own EngineSiamese + 'pytorch' CPU backend
+    # + GreedyStrategy; the oracle port only where no copy of the reference exists.
+    from oracle import ref_harness as rh
+    kind = "port"
+    ref_eng = ref_q = None
+    if rh.available() and not os.environ.get("TNQ_BENCH_REFERENCE_PORT"):
+        try:
+            ns = rh.load()
+            with rh.quiet():
+                ref_be, ref_eng = rh.make_engine(wl["dtype"], wl["K"])
+                ref_q = ns.QCTN(graph, backend=ref_be)
+                for k, v in cores.items():
+                    ref_q.cores_weights[k] = v.detach().clone().requires_grad_(True)
+            kind = "reference"
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] reference import failed ({type(exc).__name__}: {exc}); timing the oracle port", file=sys.stderr)
+            ref_eng = None
+
     def run_once(xb):
+        if ref_eng is not None:
+            with rh.quiet():
+                mx, _ = ref_eng.generate_data(xb, K=wl["K"], ret_type="TNTensor")
+                t0 = time.perf_counter()
+                if wl["mode"] == "train":
+                    ref_eng.contract_with_compiled_strategy_for_gradient(ref_q, states, mx)
+                else:
+                    with torch.no_grad():
+                        ref_eng.contract_with_compiled_strategy(ref_q, states, mx)
+                return time.perf_counter() - t0
         mx, _ = oc.generate_data(xb, wl["K"], getattr(torch, wl["dtype"]), "TNTensor")  # fresh: auto_scale is in place
         t0 = time.perf_counter()
         if wl["mode"] == "train":
@@ -178,9 +207,10 @@ def time_reference(args, wl):
     times = [step() for _ in range(n_steps)]
     total = sum(times)
     val = sample_b * len(times) / total
-    return dict(value=val, unit="samples/s", cores=threads, kind="port",
-                sample=f"{len(times)} steps of batch {sample_b} of the same network ({wl['mode']}), "
-                       f"oracle port of the reference CPU path (bit-identical to /root/reference on CPU)" + note,
+    what = ("the unmodified reference (tneq_qc EngineSiamese + 'pytorch' CPU backend + GreedyStrategy, torch.einsum left to right)"
+            if kind == "reference" else "oracle port of the reference CPU path (bit-identical to /root/reference on CPU)")
+    return dict(value=val, unit="samples/s", cores=threads, kind=kind,
+                sample=f"{len(times)} steps of batch {sample_b} of the same network ({wl['mode']}), " + what + note,
                 ms_per_step=1e3 * total / len(times), batch=sample_b)
 
 
@@ -308,10 +338,27 @@ def main():
         from tneq_b200.distributed.oneshot import OneShotAllReduce
         oneshot = OneShotAllReduce.create(n_grad + 16, dev)
 
+    checked = {"oneshot": False}
+
     def average(loss, grads):
         base = grads[0]._base if len(grads) else None
         if oneshot is not None and base is not None and base.numel() == n_grad and base.is_contiguous():
-            return oneshot.mean(base, loss.reshape(1))
+            out = oneshot.mean(base, loss.reshape(1))
+            if not checked["oneshot"]:
+                # first (warm-up) exchange on the ranks that are about to be timed: the one-shot kernel must
+                # agree with NCCL's all-reduce of the same buffers, and be bit-identical on every rank
+                checked["oneshot"] = True
+                want = torch.cat([base.detach().reshape(-1), loss.detach().reshape(1)]).clone()
+                dist.all_reduce(want)
+                want /= world
+                err = (out - want).abs().max().item()
+                ref_mag = want.abs().max().item()
+                assert err <= 2e-6 * max(ref_mag, 1e-30), f"one-shot all-reduce disagrees with NCCL: {err} vs {ref_mag}"
+                every = [torch.empty_like(out) for _ in range(world)]
+                dist.all_gather(every, out)
+                assert all(torch.equal(e, every[0]) for e in every), "one-shot all-reduce differs between ranks"
+                checked["err_vs_nccl"] = err / max(ref_mag, 1e-30)
+            return out
         flat = torch.cat([g.reshape(-1) for g in grads] + [loss.reshape(1)])
         dist.all_reduce(flat)
         flat /= world
@@ -457,11 +504,17 @@ def main():
     fp32_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
     del a, b
     kernel_ms = ms_step  # the sweep kernel is >95% of the step (profiles/ ncu launch list)
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` captures
-    # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_ladder_*.txt); cannot be measured live
-    NCU_TRAFFIC = {("cfg3", 16384): 888.6e6 + 1237.3e6, ("cfg3-fwd", 16384): 14.2e6,
-                   ("cfg2-large", 1 << 20): 604.0e6 + 7.8e6, ("cfg2-train", 1 << 18): 186.3e6 + 74.9e6}
-    traffic = NCU_TRAFFIC.get((args.workload, B)) if world == 1 else None
+    # DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
+    # `ncu --set full` capture): cannot be measured live, so it is looked up in profiles/traffic.json under
+    # the content hash of the kernel sources it was captured from -- a stale capture reads as null
+    traffic = None
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = table.get(f"{args.workload}:{B}")
+        if ent and world == 1 and ent.get("csrc_sha256") == ge.csrc_digest():
+            traffic = ent["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     achieved_tf = flops_launch / (kernel_ms * 1e-3) / 1e12
     hbm = {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9,
            "peak_gbs": peaks.get("hbm_gbs"), "source": "MEASURED_PEAKS.json (measured)" if peaks else None}
@@ -504,7 +557,8 @@ def main():
                        "parallelism": f"batch sharded over {world} GPU(s); cores replicated; "
                                       + (("one one-shot NVLink all-reduce (tnq_allreduce_oneshot, symmetric memory) of grads+loss per step"
                                           if oneshot is not None else "one packed NCCL all-reduce of grads+loss per step")
-                                         if world > 1 else "no collective")},
+                                         if world > 1 else "no collective"),
+                       "oneshot_vs_nccl_rel_err": checked.get("err_vs_nccl")},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
     if e2e is not None:
         line["e2e"] = e2e

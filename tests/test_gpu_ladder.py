@@ -154,6 +154,18 @@ def test_cfg3_full_size_properties(built_lib):
     mx, _ = eng.generate_data(x, K=K, ret_type="tensor")
     mx = [m.contiguous() * 3.0 for m in mx]           # keep typical values away from the 1e-10 clamp
     full = eng.contract_with_compiled_strategy(q, states, mx)
+    # 64 random samples of THIS batch against the oracle (the reference's algorithm on CPU, float32
+    # and float64): the full-size launch computes the same per-sample numbers as the small ones
+    gen = torch.Generator().manual_seed(2)
+    pick = torch.randperm(B, generator=gen)[:64].sort().values
+    sub = [m[pick.to(DEV)].cpu() for m in mx]
+    st_cpu = oc.unit_states(nq, K)
+    want = oc.forward(graph, cores, st_cpu, [m.clone() for m in sub])
+    truth = oc.forward(graph, {k: v.double() for k, v in cores.items()}, [s.double() for s in st_cpu],
+                       [m.double() for m in sub])
+    got = full[pick.to(DEV)].cpu()
+    assert rel_err(got, want) < 1e-5
+    assert rel_err(got.double(), truth) < max(1e-5, 3 * rel_err(want.double(), truth))
     cut = 7001
     a = eng.contract_with_compiled_strategy(q, states, [m[:cut] for m in mx])
     b = eng.contract_with_compiled_strategy(q, states, [m[cut:] for m in mx])
