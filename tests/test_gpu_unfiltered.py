@@ -92,7 +92,7 @@ def test_unfiltered_batch_error_budget(kind, n, K, B, built_lib):
     _, loss_s, grads_s = _gpu(graph, K, cores, states, mxs, sel=sel)
     err_ours = max(rel_err(g.double(), t) for g, t in zip(grads_s, tg_s))
     err_ref = max(rel_err(w.double(), t) for w, t in zip(wg_s, tg_s))
-    print(f"\\n[unfiltered {kind} n={n} B={B}] value noise: ours {noise_ours:.2e} reference {noise_ref:.2e} "
+    print(f"\n[unfiltered {kind} n={n} B={B}] value noise: ours {noise_ours:.2e} reference {noise_ref:.2e} "
           f"(largest value {truth.abs().max():.2e}); full-batch gradient error vs float64: ours {full_ours:.2e} "
           f"reference {full_ref:.2e}; on the {len(sel)} samples above the noise floor: ours {err_ours:.2e} "
           f"reference {err_ref:.2e}")
