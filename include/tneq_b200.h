@@ -127,6 +127,9 @@ int tnq_mps_ladder(int K, int n, const float* const* cores_a, const float* const
 int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                     int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
                     int accumulate, void* stream);
+/* Launch resources of one variant of the GEMM kernel: out[4] = {registers per thread, max threads per block,
+ * static shared bytes, threads per block the launch uses}. */
+int tnq_gemm_kernel_attrs(int aligned, int smallk, int* out);
 
 /*
  * Index permutation / merge / split of a dense fp32 tensor (what torch.einsum does around every

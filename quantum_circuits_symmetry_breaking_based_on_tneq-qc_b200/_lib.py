@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtneq_b200.so")
 
 EXPORTS = ["tnq_device_check", "tnq_plan_create", "tnq_plan_destroy", "tnq_plan_num_inputs",
-           "tnq_plan_num_outputs", "tnq_plan_query", "tnq_plan_run", "tnq_gemm_tf32x3", "tnq_permute_f32", "tnq_cplx_expand_f32",
+           "tnq_plan_num_outputs", "tnq_plan_query", "tnq_plan_run", "tnq_gemm_tf32x3", "tnq_gemm_kernel_attrs", "tnq_permute_f32", "tnq_cplx_expand_f32",
            "tnq_cplx_fold_f32", "tnq_mps_chain", "tnq_mps_chain_workspace_bytes", "tnq_mps_ladder",
            "tnq_mps_ladder_workspace_bytes", "tnq_allreduce_oneshot", "tnq_allreduce_oneshot_words", "tnq_allreduce_set_timeout_ms", "tnq_sgdg_step", "tnq_sgdg_step_flat", "tnq_launch_count",
            "tnq_last_error"]

@@ -10,18 +10,34 @@
 // torch.einsum per qubit group) is a real GEMM: rows = batch x kept indices, K = contracted
 // indices.  Complex contractions arrive here as real GEMMs of doubled K and N (2x2-real form).
 //
-// Kernel anatomy (one 128 x 128 output tile per CTA, 288 threads):
+// Kernel anatomy (one 128 x 128 output tile per CTA):
 //   warps 0-7  producers : 16-byte global loads of the fp32 A / B tiles (all loads of a stage are
 //                          issued before any is consumed), split into TF32 hi and lo, stored to
 //                          shared memory directly in the UMMA canonical K-major layout (8-row x
 //                          16-byte core matrices, no swizzle), 3-stage ring, fence.proxy.async +
 //                          mbarrier arrive;
-//                          afterwards the epilogue: tcgen05.ld 32 lanes x 32 columns -> registers
-//                          -> 32x33 shared-memory transpose -> one coalesced 128-byte row segment
-//                          per store instruction;
 //   warp 8     MMA issuer: one elected lane waits on the stage's "full" mbarrier and issues
 //                          4 k-steps x 3 tcgen05.mma (M=128, N=128, K=8), then tcgen05.commit to
-//                          the stage's "empty" mbarrier; owns the TMEM allocation (128 columns).
+//                          the stage's "empty" mbarrier; owns the TMEM allocation;
+//   drain (the producer warps again, while their global loads of the next stage are in flight):
+//                          every pipeline stage owns one hi*hi accumulator in TMEM; before a stage
+//                          is refilled, the partial sum its previous k-block left there is read out
+//                          (tcgen05.ld 32 lanes x 32 columns) and added, round to nearest, to a
+//                          running sum in registers; afterwards the epilogue: + the last partial
+//                          sums + the correction accumulator -> 32x33 shared-memory transpose -> one
+//                          coalesced 128-byte row segment per store instruction.
+//
+// Why the drain: the tensor core adds into its fp32 accumulator with TRUNCATION (round toward
+// zero), i.e. every accumulating MMA costs ~1/2 ulp of the accumulator, always in the same
+// direction.  Over the k-loop of one GEMM (1024 K=8 steps at bond 64) and the ~45 chained GEMMs
+// of a 16-qubit sweep this is a systematic relative bias of ~2e-4 -- outside the 1e-5 parity
+// bound.  With a FRESH accumulator per k-block (4 steps) the truncation acts on partial sums that
+// are 1/nkb of the result, and the partial sums are added with IEEE round-to-nearest on the CUDA
+// cores: the bias of a GEMM drops to ~1 ulp of its result, independent of K.  One hi*hi
+// accumulator per pipeline stage (3 x 128 TMEM columns): the "full" barrier of a stage orders the
+// drain before the next MMA into that accumulator, so no extra synchronisation is needed; the
+// 2^-11 smaller correction terms (hi*lo + lo*hi) keep one accumulator for the whole k-loop
+// (their truncation error is 2^-11 smaller too).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -40,9 +56,9 @@ constexpr int BM = 128, BN = 128, BK = 32;          // tile (BK floats = 128 byt
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB, one of {A hi, A lo, B hi, B lo}
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // 64 KB
-constexpr int PRODUCERS = 256;                      // 8 producer / epilogue warps
+constexpr int PRODUCERS = 256;                      // 8 producer / drain / epilogue warps
 constexpr int GEMM_THREADS = PRODUCERS + 32;
-constexpr uint32_t TMEM_COLS = 512;                 // 3 round-robin hi*hi accumulators + 1 for the correction terms
+constexpr uint32_t TMEM_COLS = 512;                 // one hi*hi accumulator per stage (3) + the correction accumulator
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -144,17 +160,70 @@ __device__ __forceinline__ void store_unit(float4 v, int unit, int lane, uint32_
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_base + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
 }
 
+// 32 lanes x 32 columns of an accumulator: r[j] = column c0 + j of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// running sums of one thread: its TMEM lane (= output row) x 64 columns.  first == true overwrites.
+__device__ __forceinline__ void drain_add(uint32_t taddr, float (&sum)[64], bool first) {
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)(cc * 32), r);
+        if (first) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[cc * 32 + j] = __uint_as_float(r[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[cc * 32 + j] += __uint_as_float(r[j]);   // IEEE round to nearest
+        }
+    }
+}
+
+// epilogue of one warp: 32 rows x 64 columns of sums -> C (through a 32 x 33 transpose so that a
+// store instruction covers one 128-byte row segment)
+__device__ __forceinline__ void store_tile(const float (&sum)[64], float* xpose, int lane, float* __restrict__ C,
+                                           long long ldc, long long row0, long long col0, long long M, long long N,
+                                           int accumulate) {
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xpose[lane * 33 + j] = sum[cc * 32 + j];
+        __syncwarp();
+        const long long col = col0 + cc * 32 + lane;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+            const long long row = row0 + rr;
+            if (row < M && col < N) {
+                float* d = C + row * ldc + col;
+                const float v = xpose[rr * 33 + lane];
+                *d = accumulate ? *d + v : v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // SMALLK (K <= 256: a handful of k-blocks, the regime of the bond-64 sweep where K = 2 x bond):
-// one pipeline stage, 2 accumulators (hi*hi + correction) = 256 TMEM columns and <= 112 registers,
-// so that TWO CTAs share an SM and one tile's epilogue overlaps the other tile's loads and MMAs --
-// with a single resident CTA the tensor core idles through every prologue and epilogue.
+// one pipeline stage, one hi*hi + one correction accumulator = 256 TMEM columns and <= 112
+// registers, so that TWO CTAs share an SM and one tile's epilogue overlaps the other tile's loads
+// and MMAs.
 template <bool ALIGNED, bool SMALLK>
-__global__ void __launch_bounds__(GEMM_THREADS, SMALLK ? 2 : 1)
+__global__ void __maxnreg__(SMALLK ? 112 : 168)
 tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, long long M,
                        long long N, long long K, long long lda, long long ldb, long long ldc, long long strideA,
                        long long strideB, long long strideC, int accumulate) {
-    constexpr int NSTAGE = SMALLK ? 1 : STAGES;
-    constexpr int NACC = SMALLK ? 1 : 3;                 // round-robin hi*hi accumulators; the correction one follows
+    constexpr int NSTAGE = SMALLK ? 1 : STAGES;          // pipeline stages = hi*hi accumulators (the correction one follows)
     constexpr uint32_t NCOLS = SMALLK ? 256u : TMEM_COLS;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[2 * STAGES + 1];
@@ -184,87 +253,72 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t tmem_corr = tmem_base + (uint32_t)(NSTAGE * BN);
     const int nkb = (int)((K + BK - 1) / BK);
 
     if (warp < PRODUCERS / 32) {
-        // ---------------- producers ----------------
+        // ---------------- producers (+ drain) ----------------
+        // warp w owns TMEM lanes [32 (w % 4), +32) (hardware rule) x the column half w / 4
+        const int quad = warp & 3, chalf = warp >> 2;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * 64);
+        float sum[64];
+        bool have = false;                    // sum[] holds at least one partial result
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % NSTAGE;
             const uint32_t phase = (uint32_t)(kb / NSTAGE) & 1u;
-            mbar_wait(empty0 + 8 * s, phase ^ 1u);
+            mbar_wait(empty0 + 8 * s, phase ^ 1u);           // the MMAs of k-block kb - NSTAGE have retired
             const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
             const long long k0 = (long long)kb * BK;
-            float4 va[4], vb[4];
+            if (SMALLK) {
+                if (kb >= NSTAGE) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    drain_add(tlane + (uint32_t)(s * BN), sum, !have);
+                    have = true;
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                }
+                float4 v[4];                  // A then B: half the registers in flight
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {        // all global loads of the stage first ...
-                va[i] = load_unit<ALIGNED>(A + k0, lda, M - m0, K - k0, warp * 4 + i, lane);
-                vb[i] = load_unit<ALIGNED>(B + k0, ldb, N - n0, K - k0, warp * 4 + i, lane);
-            }
+                for (int i = 0; i < 4; ++i) v[i] = load_unit<ALIGNED>(A + k0, lda, M - m0, K - k0, warp * 4 + i, lane);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {        // ... then split and store
-                store_unit(va[i], warp * 4 + i, lane, st, st + TILE_BYTES);
-                store_unit(vb[i], warp * 4 + i, lane, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
-            mbar_arrive(full0 + 8 * s);
-        }
-        // ---------------- epilogue ----------------
-        // warp w reads TMEM lanes [32 (w % 4), +32) (hardware rule) and the column half w / 4
-        mbar_wait(accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quad = warp & 3, chalf = warp >> 2;
-        float* xpose = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // pipeline smem is idle now
-        const long long row0 = m0 + quad * 32;
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-            const int c0 = chalf * 64 + cc * 32;
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float acc[32];
+                for (int i = 0; i < 4; ++i) store_unit(v[i], warp * 4 + i, lane, st, st + TILE_BYTES);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-#pragma unroll 1
-            for (int extra = 1; extra <= NACC; ++extra) {
-                if (extra < NACC && nkb * (BK / 8) <= extra) continue;   // that accumulator was never written
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr + (uint32_t)(extra * BN)));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int i = 0; i < 4; ++i) v[i] = load_unit<ALIGNED>(B + k0, ldb, N - n0, K - k0, warp * 4 + i, lane);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
-            }
-            // lane = row of the 32 x 32 block: transpose so that a store instruction covers one row
+                for (int i = 0; i < 4; ++i) store_unit(v[i], warp * 4 + i, lane, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
+            } else {
+                float4 va[4], vb[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) xpose[lane * 33 + j] = acc[j];
-            __syncwarp();
-            const long long col = n0 + c0 + lane;
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-                const long long row = row0 + rr;
-                if (row < M && col < N) {
-                    float* d = C + row * ldc + col;
-                    const float v = xpose[rr * 33 + lane];
-                    *d = accumulate ? *d + v : v;
+                for (int i = 0; i < 4; ++i) {        // all global loads of the stage first ...
+                    va[i] = load_unit<ALIGNED>(A + k0, lda, M - m0, K - k0, warp * 4 + i, lane);
+                    vb[i] = load_unit<ALIGNED>(B + k0, ldb, N - n0, K - k0, warp * 4 + i, lane);
+                }
+                if (kb >= NSTAGE) {                  // ... the drain of this stage's accumulator while they are in flight ...
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    drain_add(tlane + (uint32_t)(s * BN), sum, !have);
+                    have = true;
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {        // ... then split and store
+                    store_unit(va[i], warp * 4 + i, lane, st, st + TILE_BYTES);
+                    store_unit(vb[i], warp * 4 + i, lane, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
                 }
             }
-            __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
+            mbar_arrive(full0 + 8 * s);          // (also: this stage's accumulator has been read)
         }
+        // ---------------- epilogue ----------------
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int pending = nkb < NSTAGE ? nkb : NSTAGE;     // accumulators that still hold a partial sum
+#pragma unroll 1
+        for (int i = 0; i < pending; ++i) {
+            drain_add(tlane + (uint32_t)(((nkb - pending + i) % NSTAGE) * BN), sum, !have);
+            have = true;
+        }
+        drain_add(tmem_corr - tmem_base + tlane, sum, false);   // correction terms
+        float* xpose = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // pipeline smem is idle now
+        store_tile(sum, xpose, lane, C, ldc, m0 + quad * 32, n0 + chalf * 64, M, N, accumulate);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
         // ---------------- MMA issuer ----------------
@@ -275,25 +329,21 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
+                const uint32_t tmem_h = tmem_base + (uint32_t)(s * BN);
 #pragma unroll
                 for (int j = 0; j < BK / 8; ++j) {
                     const uint32_t ko = (uint32_t)j * 2u * 128u;     // two 16-byte chunks per K=8 step
                     const uint64_t a_hi = umma_desc(st + ko), a_lo = umma_desc(st + TILE_BYTES + ko);
                     const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES + ko), b_lo = umma_desc(st + 3 * TILE_BYTES + ko);
-                    // The tensor core truncates (round-toward-zero) when it adds into the fp32
-                    // accumulator; every add costs ~1/2 ulp of the ACCUMULATOR.  The correction
-                    // terms are 2^-11 smaller, so they get their own accumulator (their truncation
-                    // errors are 2^-11 smaller too) and the two are summed once, round-to-nearest,
-                    // in the epilogue (Ootomo & Yokota's split-accumulator scheme).
-                    // The hi*hi products themselves are spread round-robin over three accumulators,
-                    // which cuts the length of every truncating chain by three.
-                    const int step = kb * (BK / 8) + j;
-                    umma_tf32(tmem_base + NACC * BN, a_lo, b_hi, step != 0);
-                    umma_tf32(tmem_base + NACC * BN, a_hi, b_lo, 1u);
-                    umma_tf32(tmem_base + (uint32_t)(step % NACC) * BN, a_hi, b_hi, step >= NACC);
+                    // correction terms: one accumulator for the whole k-loop (Ootomo & Yokota's split
+                    // accumulators); hi*hi: a fresh accumulator per k-block, drained and summed round-to-
+                    // nearest on the CUDA cores (header comment)
+                    umma_tf32(tmem_corr, a_lo, b_hi, (kb | j) != 0);
+                    umma_tf32(tmem_corr, a_hi, b_lo, 1u);
+                    umma_tf32(tmem_h, a_hi, b_hi, j != 0);
                 }
-                umma_commit(empty0 + 8 * s);                          // frees the stage when the MMAs retire
-                if (kb == nkb - 1) umma_commit(accum_bar);            // accumulator complete
+                umma_commit(empty0 + 8 * s);                          // frees the stage (and its accumulator) when the MMAs retire
+                if (kb == nkb - 1) umma_commit(accum_bar);            // everything complete
             }
             __syncwarp();
         }
@@ -305,6 +355,19 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
 }
 
 }  // namespace
+
+// launch resources of one kernel variant (tests / diagnostics): out = {registers per thread, max threads per block,
+// static shared bytes, threads the launch uses}
+extern "C" int tnq_gemm_kernel_attrs(int aligned, int smallk, int* out) {
+    auto kern = smallk ? (aligned ? tnq_gemm_tf32x3_kernel<true, true> : tnq_gemm_tf32x3_kernel<false, true>)
+                       : (aligned ? tnq_gemm_tf32x3_kernel<true, false> : tnq_gemm_tf32x3_kernel<false, false>);
+    cudaFuncAttributes at;
+    const cudaError_t e = cudaFuncGetAttributes(&at, kern);
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncGetAttributes(gemm)");
+    out[0] = at.numRegs, out[1] = at.maxThreadsPerBlock, out[2] = (int)at.sharedSizeBytes;
+    out[3] = GEMM_THREADS;
+    return 0;
+}
 
 extern "C" int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                                int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB,

@@ -1,0 +1,1015 @@
+// tnq_ladder2_core.cuh -- second-generation sweep of the TWO-LAYER merged MPS network (BASELINE cfg3,
+// QCTN.merge(mps_n, mps_n), tneq_qc/core/qctn.py:1296-1506), real float32, edge rank K = 3.
+// Same mathematics as tnq_ladder_core.cuh (the per-qubit group of the greedy sweep,
+// tneq_qc/contractor/greedy_strategy.py:690-990: phases A, B, C below; the fused loss of
+// tneq_qc/core/engine_siamese.py:490-530; its reverse sweep), different mapping:
+//
+//   * a LANE is a SAMPLE.  A CTA of 4 warps owns a tile of S = 32 / R samples; the 32 lanes of a warp
+//     are R "slots" x S samples and the slots of a warp work on different ROW BLOCKS of the same step.
+//     Everything that lives per sample is laid out [element][position][sample], so every shared-memory
+//     access of a warp is R runs of S consecutive words: conflict free and broadcast free by
+//     construction (the position maps below put the row blocks a warp works on at the same time into
+//     different banks).
+//   * everything that is shared by all samples (the core tensors, folded with the circuit states) sits in
+//     CONSTANT memory: the operands arrive through the uniform datapath (LDCU -> uniform registers ->
+//     FFMA2 with a uniform operand), never through the load/store unit.
+//   * the environment E (K^6 floats per sample) never exists in memory: with row block (o,q',r)
+//         V[f,g',i']  = sum_p' T2[f,o,g',p'] U[i',p',q',r]                    (phase C, first half)
+//         E'[f,h,j]   = sum_{g',i'} V[f,g',i'] X[g',h,i',j]                   (phase C, second half)
+//         T1'[f",j]   = sum_{f,h} Bs'[f,h,f"] E'[f,h,j]                       (phase A of the NEXT step)
+//     are one pass over registers (27 row blocks of 405 multiply-adds); only T1' (K^5), T2 (K^4) and
+//     U (K^4) go through shared memory.  The reverse sweep re-derives E' from the checkpointed T2 the
+//     same way, so the only per-sample state that ever reaches HBM is T2 (81 floats per step).
+//   * all hot loops are "vector += scalar * vector" on packed fp32 pairs (fma.rn.f32x2, tnq_f2.cuh).
+//
+// Per step q (0 <= q <= n-2), with Bs_q[c,e,f] = sum_d A_q[c,d,e,f] s_{q+1}[d]  (q >= 1),
+// As0[e,f] = sum_{c,d} A_0[c,d,e,f] s_0[c] s_1[d], E_q[c,l,n,p,e,g] the environment entering step q:
+//   A1: T1_q[f,l,n,p,g]      = sum_{c,e} Bs_q[c,e,f] E_q[c,l,n,p,e,g]
+//   A2: T2_q[f,o,g,p]        = sum_{l,n} Bs_q[l,n,o] T1_q[f,l,n,p,g]          (T2_0 = As0[g,f] As0[p,o])
+//   B : U_q[i,p,q',r]        = sum_k M_q[i,k] X_q[p,q',k,r]
+//   C : E_{q+1}[f,o,q',r,h,j] = sum_{g,i,p} T2_q[f,o,g,p] U_q[i,p,q',r] X_q[g,h,i,j]
+// and for the last step q = n-2 (einsum "cdef,gfhi,ahj,klmn,onjp,aekocgm,d,l->api" then "acd,adc->a"):
+//   value = sum T2[f,o,g,p0] X[g,f,h,i] M_{n-2}[h,j] X[p0,o,j,p'] M_{n-1}[i,p'].
+//
+// Shared by the CUDA kernels (tnq_ladder2.cu) and by a thread-by-thread CPU emulation that the tests
+// build to check this exact code without a GPU (tests/emu/ladder2_emu.cpp).
+#pragma once
+
+#include "tnq_ladder_core.cuh"   // Args, Vec<N>, axpy, dot, ldg_f, TNQ_* macros
+
+namespace tnq_l2 {
+
+using tnq_ladder::Args;
+using tnq_ladder::Vec;
+using tnq_ladder::axpy;
+using tnq_ladder::dot;
+using tnq_ladder::ldg_f;
+using tnq_ladder::MAXQ;
+
+constexpr int K = 3, K2 = 9, K3 = 27, K4 = 81;
+constexpr int NW = 4, NT = 128;                  // warps / threads per CTA
+
+// ---- constant pool (floats) ------------------------------------------------------------------------
+// one block per step q, then a tail with the extra layouts of the last step and As0
+constexpr int C_XA = 0;      // XA[(g,i)][(h,j)] = X_q[g,h,i,j], row pitch 10
+constexpr int C_XB = 90;     // XB[(h,j)][(g,i)] = X_q[g,h,i,j], row pitch 10
+constexpr int C_BA = 180;    // BA[(c,e)][f]     = Bs_q[c,e,f],  row pitch 4
+constexpr int C_BB = 216;    // BB[o][(l,n)]     = Bs_q[l,n,o],  row pitch 10
+constexpr int C_STEP = 248;
+constexpr int T_XN = 0;      // XN[(a,b)][(c,d)] = X_{n-2}[a,b,c,d], row pitch 10
+constexpr int T_XC = 90;     // XC[(c,d)][(a,b)] = X_{n-2}[a,b,c,d], row pitch 10
+constexpr int T_AS0 = 180;   // As0[e][f]
+constexpr int C_TAIL = 192;
+constexpr int C_MAX = (MAXQ - 1) * C_STEP + C_TAIL;      // 15816 floats < 64 KB
+TNQ_HOSTDEV constexpr int cst_floats(int n) { return (n - 1) * C_STEP + C_TAIL; }
+
+// element idx of the constant pool, from the caller's cores and circuit states
+TNQ_HD float cst_element(const Args& a, int idx) {
+    const int n = a.n;
+    if (idx >= (n - 1) * C_STEP) {
+        const int t = idx - (n - 1) * C_STEP;
+        const float* X = a.coreX[n - 2];
+        if (t < T_XC) {
+            const int r = t / 10, col = t % 10;
+            return col < 9 ? X[r * 9 + col] : 0.f;
+        }
+        if (t < T_AS0) {
+            const int r = (t - T_XC) / 10, col = (t - T_XC) % 10;
+            return col < 9 ? X[col * 9 + r] : 0.f;
+        }
+        if (t < T_AS0 + K2) {                    // As0[e][f] = sum_{c,d} A_0[c,d,e,f] s0[c] s1[d]
+            const int ef = t - T_AS0;
+            float v = 0.f;
+            for (int c = 0; c < K; ++c)
+                for (int d = 0; d < K; ++d) v = fmaf(a.coreA[0][(c * K + d) * K2 + ef], a.state[0][c] * a.state[1][d], v);
+            return v;
+        }
+        return 0.f;
+    }
+    const int q = idx / C_STEP, t = idx % C_STEP;
+    const float* X = a.coreX[q];
+    if (t < C_XB) {                              // XA[(g,i)][(h,j)]
+        const int gi = t / 10, hj = t % 10;
+        if (hj >= 9) return 0.f;
+        return X[(((gi / 3) * 3 + hj / 3) * 3 + gi % 3) * 3 + hj % 3];
+    }
+    if (t < C_BA) {                              // XB[(h,j)][(g,i)]
+        const int hj = (t - C_XB) / 10, gi = (t - C_XB) % 10;
+        if (gi >= 9) return 0.f;
+        return X[(((gi / 3) * 3 + hj / 3) * 3 + gi % 3) * 3 + hj % 3];
+    }
+    if (q == 0) return 0.f;
+    int c, e, f;
+    if (t < C_BB) {                              // BA[(c,e)][f]
+        const int ce = (t - C_BA) / 4;
+        f = (t - C_BA) % 4;
+        c = ce / 3, e = ce % 3;
+    } else if (t < C_BB + 30) {                  // BB[o][(l,n)]: Bs[l,n,o]
+        f = (t - C_BB) / 10;
+        const int ln = (t - C_BB) % 10;
+        if (ln >= 9) return 0.f;
+        c = ln / 3, e = ln % 3;
+    } else {
+        return 0.f;
+    }
+    if (f >= K) return 0.f;
+    float v = 0.f;                               // Bs[c][e][f] = sum_d A_q[c][d][e][f] s_{q+1}[d]
+    for (int d = 0; d < K; ++d) v = fmaf(a.coreA[q][((c * K + d) * K + e) * K + f], a.state[q + 1][d], v);
+    return v;
+}
+
+// ---- geometry of one variant: R slots x S samples per warp ----------------------------------------------
+template <int R>
+struct Geo {
+    static_assert(R == 1 || R == 2 || R == 4 || R == 8, "slots per warp");
+    static constexpr int S = 32 / R;                         // samples per tile
+    static constexpr int NU = (K3 + R - 1) / R;              // units (groups of R row blocks) per step
+    static constexpr int PO = R == 1 ? 3 : (R == 8 ? 8 : 4);  // padded extent of the o / r position
+    static constexpr int PQ = R == 1 ? 9 : (R == 2 ? 10 : (R == 4 ? 12 : 16));   // ... of the (q',r) position
+    static constexpr int SP = S + 1;                         // pitch of the per-sample row buffers
+    // shared-memory map (floats)
+    static constexpr int T2_SZ = K3 * PO * S, U_SZ = K2 * PQ * S, T1_SZ = K2 * NU * 32, M_SZ = K2 * S;
+    static constexpr int OFF_T2 = 0, OFF_U = OFF_T2 + T2_SZ, OFF_T1 = OFF_U + U_SZ, OFF_MA = OFF_T1 + T1_SZ,
+                         OFF_MB = OFF_MA + M_SZ, OFF_VAL = OFF_MB + M_SZ;
+    static constexpr int VAL_SZ = K2 * S + 2 * S + 32;        // last step: partial values | value | d value; misc
+    static constexpr int FWD_FLOATS = OFF_VAL + VAL_SZ;
+    // training only
+    static constexpr int OFF_DT2R = FWD_FLOATS;              // d T2 of the step above, [o''][f''][g] x position of p
+    static constexpr int OFF_DT2P = OFF_DT2R + T2_SZ;        // per-thread partial sums of d T2, two flush slots
+    static constexpr int DT2P_SZ = K3 * 2 * NT;
+    static constexpr int OFF_DUP = OFF_DT2P + DT2P_SZ;       // per-row-block partial sums of d U
+    static constexpr int OFF_P2P = OFF_DUP + T1_SZ;          // per-row-block part 2 of d Bs
+    static constexpr int P2P_SZ = K * NU * 32;
+    static constexpr int OFF_FL = OFF_P2P + P2P_SZ;          // per-warp flush scratch [27][33]; later the row buffers
+    static constexpr int FL_SZ = NW * K3 * 33;
+    static constexpr int OFF_WS = OFF_FL + FL_SZ;            // per-warp row sums [NW][108]
+    static constexpr int WS_SZ = NW * 108;
+    static constexpr int OFF_SRC = OFF_WS + WS_SZ;           // flush-slot bookkeeping (ints)
+    static constexpr int SRC_SZ = 3 * 64 + 4 + NW * R * 2;
+    static constexpr int TRAIN_FLOATS = OFF_SRC + SRC_SZ;
+    static_assert(FL_SZ >= K4 * SP + K2 * SP, "row buffers alias the flush scratch");
+    // global checkpoint of one tile: T2_q for q = 1 .. n-2, laid out like the shared copy
+    TNQ_HOSTDEV static constexpr long long ckpt_floats(int n) { return (long long)(n - 2) * T2_SZ; }
+};
+// per-tile gradient slice: step q at q * GQ: [0,81) dX (left copy) | [81,162) dX (right copy) |
+// [162,189) dBs part 1 | [189,216) dBs part 2;  step 0: [162,171) dAs0
+constexpr int GQ = 216;
+TNQ_HOSTDEV constexpr int grad_floats(int n) { return (n - 1) * GQ; }
+
+// ---- row blocks: unit u, slot -> rb = o*9 + q'*3 + r (or -1: idle) -----------------------------------
+// Built so that the row blocks of one unit have o / (q',r) / r positions that are pairwise equal or fall
+// into different bank groups (tests/test_ladder2_emu.py checks this exhaustively).
+template <int R>
+TNQ_HD int rb_of(int u, int slot) {
+    if (R == 1) return u;
+    if (R == 2) {
+        if (u < 9) return (u / 3) * 9 + slot * 3 + (u % 3);            // (o, q' = slot, r)
+        if (u < 12) return slot * 9 + 6 + (u - 9);                     // (o = slot, q' = 2, r)
+        if (u == 12) return 24 + slot;                                 // (2, 2, r = slot)
+        return slot == 0 ? 26 : -1;
+    }
+    if (R == 4) {
+        if (u < 6) {
+            const int o = u >> 1;
+            int qr;
+            if ((u & 1) == 0) qr = (slot >> 1) * 3 + (slot & 1);       // q' in {0,1} x r in {0,1}
+            else qr = slot == 0 ? 2 : (slot == 1 ? 5 : (slot == 2 ? 6 : 7));
+            return o * 9 + qr;
+        }
+        return slot < 3 ? slot * 9 + 8 : -1;
+    }
+    if (u < 3) return u * 9 + slot;
+    return slot < 3 ? slot * 9 + 8 : -1;
+}
+// inverse: rb -> (unit, slot)
+template <int R>
+TNQ_HD void uslot_of(int rb, int& u, int& slot) {
+    const int o = rb / 9, qr = rb % 9, qq = qr / 3, r = qr % 3;
+    if (R == 1) {
+        u = rb, slot = 0;
+    } else if (R == 2) {
+        if (qq < 2) u = o * 3 + r, slot = qq;
+        else if (o < 2) u = 9 + r, slot = o;
+        else if (r < 2) u = 12, slot = r;
+        else u = 13, slot = 0;
+    } else if (R == 4) {
+        if (qr == 8) {
+            u = 6, slot = o;
+        } else if (qq < 2 && r < 2) {
+            u = o * 2, slot = qq * 2 + r;
+        } else {
+            u = o * 2 + 1, slot = qr == 2 ? 0 : (qr == 5 ? 1 : (qr == 6 ? 2 : 3));
+        }
+    } else {
+        if (qr == 8) u = 3, slot = o;
+        else u = o, slot = qr;
+    }
+}
+template <int R>
+TNQ_HD int pos_q(int qr) {                       // position of (q',r) in the U layout
+    if (R == 4) return qr == 2 ? 4 : (qr == 3 ? 2 : (qr == 4 ? 3 : qr));
+    return qr;
+}
+// units [ustart(w), ustart(w+1)) belong to warp w
+template <int R>
+TNQ_HD int ustart(int w) {
+    if (R == 1) return w == 0 ? 0 : (w == 1 ? 7 : (w == 2 ? 14 : (w == 3 ? 21 : 27)));
+    if (R == 2) return w == 0 ? 0 : (w == 1 ? 4 : (w == 2 ? 8 : (w == 3 ? 11 : 14)));
+    if (R == 4) return w == 0 ? 0 : (w == 1 ? 2 : (w == 2 ? 4 : (w == 3 ? 6 : 7)));
+    return w;
+}
+
+// ---- context -----------------------------------------------------------------------------------------
+struct Ctx {
+    float* sm;                  // the CTA's shared memory
+    const float* cst;           // constant pool (CPU emulation; the device reads the __constant__ copy)
+    const Args* a;
+    long long B, b0;            // batch size, first sample of the tile
+    float* ck;                  // this CTA's T2 checkpoint slab (global)
+    float* gpart;               // this TILE's gradient slice (global)
+    float* lpart;               // this tile's loss partial
+    const float* seed;          // MODE 2
+    float* values;
+    float log_scale, inv_count;
+};
+
+// per-thread state that lives across phases of the reverse sweep (registers on the device)
+struct TS {
+    Vec<K2> accX[K2];           // d X: [(g',i')] over (h,j)   (last step: [(p0,o)] over (j,p'))
+    Vec<K> accB[K2];            // d Bs part 1: [(f,h)] over f''
+};
+
+#ifdef __CUDA_ARCH__
+#define TNQ2_CST(off) tnq_l2_cst_dev[(off)]
+#else
+#define TNQ2_CST(off) c.cst[(off)]
+#endif
+
+}  // namespace tnq_l2
+
+#ifdef __CUDACC__
+// (this header is included by exactly one translation unit: tnq_ladder2.cu)
+__constant__ float tnq_l2_cst_dev[tnq_l2::C_MAX + 8];
+#endif
+
+namespace tnq_l2 {
+
+// N floats of the constant pool starting at an EVEN offset (warp-uniform on the device)
+template <int N>
+TNQ_HD void cvec(const Ctx& c, Vec<N>& v, int off) {
+    (void)c;
+    TNQ_UNROLL
+    for (int i = 0; i < Vec<N>::NP; ++i) v.p[i] = tnq_ladder::F2{TNQ2_CST(off + 2 * i), TNQ2_CST(off + 2 * i + 1)};
+    if (N & 1) v.s = TNQ2_CST(off + N - 1);
+    else v.s = 0.f;
+}
+
+TNQ_HD float load_m(const Ctx& c, int q, long long b, int it) {
+    return b < c.B ? ldg_f(c.a->mx[q] + b * c.a->mx_stride[q] + it) : 0.f;
+}
+
+// ================================= forward phases ======================================================
+
+// T2_0 = As0 (x) As0 for every sample of the tile
+template <int R>
+TNQ_HD void fill_t2_first(const Ctx& c, int tid) {
+    using G = Geo<R>;
+    float* T2s = c.sm + G::OFF_T2;
+    const int base = (c.a->n - 1) * C_STEP + T_AS0;
+    for (int e = tid; e < K4 * G::S; e += NT) {
+        const int s = e % G::S, x = e / G::S;          // x = ((p*3 + f)*3 + g)*3 + o
+        const int o = x % 3, g = (x / 3) % 3, f = (x / 9) % 3, p = x / 27;
+        T2s[((p * 9 + f * 3 + g) * G::PO + o) * G::S + s] = TNQ2_CST(base + g * 3 + f) * TNQ2_CST(base + p * 3 + o);
+    }
+}
+
+// phase B: U_q from M_q (task = (i, sample))
+template <int R>
+TNQ_HD void phase_u(const Ctx& c, int q, int tid) {
+    using G = Geo<R>;
+    float* Us = c.sm + G::OFF_U;
+    const int cq = q * C_STEP;
+    TNQ_NOUNROLL
+    for (int t = tid; t < K * G::S; t += NT) {
+        const int i = t / G::S, s = t % G::S;
+        float m[K];
+        TNQ_UNROLL
+        for (int k = 0; k < K; ++k) m[k] = load_m(c, q, c.b0 + s, i * K + k);
+        TNQ_UNROLL
+        for (int p = 0; p < K; ++p) {
+            Vec<K2> u;
+            u.zero();
+            TNQ_UNROLL
+            for (int k = 0; k < K; ++k) {
+                Vec<K2> xa;
+                cvec<K2>(c, xa, cq + C_XA + (p * 3 + k) * 10);     // X[p,q',k,r] over (q',r)
+                axpy(u, m[k], xa);
+            }
+            TNQ_UNROLL
+            for (int qr = 0; qr < K2; ++qr) Us[((i * 3 + p) * G::PQ + pos_q<R>(qr)) * G::S + s] = u.get(qr);
+        }
+    }
+}
+
+// copy of M_q for the tasks that share it: Ms[(row*3+col)][sample]
+template <int R>
+TNQ_HD void load_ms(const Ctx& c, int q, float* Ms, int tid) {
+    using G = Geo<R>;
+    for (int e = tid; e < K2 * G::S; e += NT) Ms[e] = load_m(c, q, c.b0 + e % G::S, e / G::S);
+}
+
+// phase A2: T2_q from T1_q (task = (f, p, g, sample)); training keeps a copy in the checkpoint slab
+template <int R, bool CK>
+TNQ_HD void phase_a2(const Ctx& c, int q, int tid) {
+    using G = Geo<R>;
+    const float* T1s = c.sm + G::OFF_T1;
+    float* T2s = c.sm + G::OFF_T2;
+    const int cq = q * C_STEP;
+    TNQ_NOUNROLL
+    for (int t = tid; t < K3 * G::S; t += NT) {
+        const int s = t % G::S, x = t / G::S;              // x = (f*3 + p)*3 + g
+        const int g = x % 3, p = (x / 3) % 3, f = x / 9;
+        Vec<K> acc;
+        acc.zero();
+        TNQ_UNROLL
+        for (int ln = 0; ln < K2; ++ln) {
+            int u, slot;
+            uslot_of<R>(ln * 3 + p, u, slot);
+            const float v = T1s[((f * 3 + g) * G::NU + u) * 32 + slot * G::S + s];
+            Vec<K> b;
+            cvec<K>(c, b, cq + C_BA + ln * 4);             // Bs[l,n,o] over o
+            axpy(acc, v, b);
+        }
+        TNQ_UNROLL
+        for (int o = 0; o < K; ++o) {
+            const int at = ((p * 9 + f * 3 + g) * G::PO + o) * G::S + s;
+            T2s[at] = acc.get(o);
+            if (CK) c.ck[(long long)(q - 1) * G::T2_SZ + at] = acc.get(o);
+        }
+    }
+}
+
+// this thread's operands of one row block
+template <int R>
+struct RowBlock {
+    int o, qr, u;
+    const float* t2;            // + ((p'*9 + f*3+g') * PO) * S
+    const float* uu;            // + ((i'*3+p') * PQ) * S
+};
+template <int R>
+TNQ_HD bool row_block(const Ctx& c, int u, int lane, RowBlock<R>& rb) {
+    using G = Geo<R>;
+    const int slot = lane / G::S, s = lane % G::S;
+    const int id = rb_of<R>(u, slot);
+    if (id < 0) return false;
+    rb.o = id / 9, rb.qr = id % 9, rb.u = u;
+    rb.t2 = c.sm + G::OFF_T2 + rb.o * G::S + s;
+    rb.uu = c.sm + G::OFF_U + pos_q<R>(rb.qr) * G::S + s;
+    return true;
+}
+
+// V[i'] over (f,g') = sum_p' T2[f,o,g',p'] U[i',p',q',r]
+template <int R>
+TNQ_HD void make_v(const RowBlock<R>& rb, const float (&u9)[K2], Vec<K2> (&V)[K]) {
+    using G = Geo<R>;
+    TNQ_UNROLL
+    for (int i = 0; i < K; ++i) V[i].zero();
+    TNQ_UNROLL
+    for (int p = 0; p < K; ++p) {
+        Vec<K2> t;
+        TNQ_UNROLL
+        for (int fg = 0; fg < K2; ++fg) t.set(fg, rb.t2[(p * 9 + fg) * G::PO * G::S]);
+        TNQ_UNROLL
+        for (int i = 0; i < K; ++i) axpy(V[i], u9[i * 3 + p], t);
+    }
+}
+// E'[f] over (h,j) = sum_{g',i'} V[i'][(f,g')] X_q[g',h,i',j]
+TNQ_HD void make_e(const Ctx& c, int cq, const Vec<K2> (&V)[K], Vec<K2> (&E)[K]) {
+    TNQ_UNROLL
+    for (int f = 0; f < K; ++f) E[f].zero();
+    TNQ_UNROLL
+    for (int g = 0; g < K; ++g)
+        TNQ_UNROLL
+        for (int i = 0; i < K; ++i) {
+            Vec<K2> xa;
+            cvec<K2>(c, xa, cq + C_XA + (g * 3 + i) * 10);
+            TNQ_UNROLL
+            for (int f = 0; f < K; ++f) axpy(E[f], V[i].get(f * 3 + g), xa);
+        }
+}
+
+// fused phase C of step q and phase A1 of step q+1, one row block (o,q',r) at a time
+template <int R>
+TNQ_HD void phase_c_a1(const Ctx& c, int q, int warp, int lane) {
+    using G = Geo<R>;
+    float* T1s = c.sm + G::OFF_T1;
+    const int cq = q * C_STEP, cq1 = (q + 1) * C_STEP;
+    TNQ_NOUNROLL
+    for (int u = ustart<R>(warp); u < ustart<R>(warp + 1); ++u) {
+        RowBlock<R> rb;
+        if (!row_block<R>(c, u, lane, rb)) continue;
+        float u9[K2];
+        TNQ_UNROLL
+        for (int x = 0; x < K2; ++x) u9[x] = rb.uu[x * G::PQ * G::S];
+        Vec<K2> V[K], E[K];
+        make_v<R>(rb, u9, V);
+        make_e(c, cq, V, E);
+        Vec<K> T1[K];                      // [j] over f''
+        TNQ_UNROLL
+        for (int j = 0; j < K; ++j) T1[j].zero();
+        TNQ_UNROLL
+        for (int fh = 0; fh < K2; ++fh) {
+            Vec<K> b;
+            cvec<K>(c, b, cq1 + C_BA + fh * 4);            // Bs'[f,h,f''] over f''
+            TNQ_UNROLL
+            for (int j = 0; j < K; ++j) axpy(T1[j], E[fh / 3].get((fh % 3) * 3 + j), b);
+        }
+        TNQ_UNROLL
+        for (int f2 = 0; f2 < K; ++f2)
+            TNQ_UNROLL
+            for (int j = 0; j < K; ++j) T1s[((f2 * 3 + j) * G::NU + u) * 32 + lane] = T1[j].get(f2);
+    }
+}
+
+// last step, shared by the forward and the reverse pass: L[j][p'] and Z over (p0,o) of task (g,f)
+template <int R>
+TNQ_HD void last_lz(const Ctx& c, int gf, int s, float (&mh)[K][K], float (&mi)[K][K], float (&L)[K][K], Vec<K2>& Z) {
+    using G = Geo<R>;
+    const int n = c.a->n;
+    const float* MA = c.sm + G::OFF_MA;
+    const float* MB = c.sm + G::OFF_MB;
+    float x[K][K];
+    TNQ_UNROLL
+    for (int h = 0; h < K; ++h)
+        TNQ_UNROLL
+        for (int i = 0; i < K; ++i) {
+            x[h][i] = ldg_f(c.a->coreX[n - 2] + gf * K2 + h * 3 + i);
+            mh[h][i] = MA[(h * 3 + i) * G::S + s];
+            mi[h][i] = MB[(h * 3 + i) * G::S + s];
+        }
+    float tmp[K][K];                       // [h][p'] = sum_i x[h][i] Mi[i][p']
+    TNQ_UNROLL
+    for (int h = 0; h < K; ++h)
+        TNQ_UNROLL
+        for (int pp = 0; pp < K; ++pp) {
+            float v = 0.f;
+            TNQ_UNROLL
+            for (int i = 0; i < K; ++i) v = fmaf(x[h][i], mi[i][pp], v);
+            tmp[h][pp] = v;
+        }
+    TNQ_UNROLL
+    for (int j = 0; j < K; ++j)
+        TNQ_UNROLL
+        for (int pp = 0; pp < K; ++pp) {
+            float v = 0.f;
+            TNQ_UNROLL
+            for (int h = 0; h < K; ++h) v = fmaf(mh[h][j], tmp[h][pp], v);
+            L[j][pp] = v;
+        }
+    Z.zero();
+    const int tail = (n - 1) * C_STEP;
+    TNQ_UNROLL
+    for (int jp = 0; jp < K2; ++jp) {
+        Vec<K2> xc;
+        cvec<K2>(c, xc, tail + T_XC + jp * 10);            // X[p0,o,j,p'] over (p0,o)
+        axpy(Z, L[jp / 3][jp % 3], xc);
+    }
+}
+
+template <int R>
+TNQ_HD void last_fwd(const Ctx& c, int tid) {
+    using G = Geo<R>;
+    const float* T2s = c.sm + G::OFF_T2;
+    float* valp = c.sm + G::OFF_VAL;
+    TNQ_NOUNROLL
+    for (int t = tid; t < K2 * G::S; t += NT) {
+        const int gf = t / G::S, s = t % G::S, g = gf / 3, f = gf % 3;
+        float mh[K][K], mi[K][K], L[K][K];
+        Vec<K2> Z;
+        last_lz<R>(c, gf, s, mh, mi, L, Z);
+        float v = 0.f;
+        TNQ_UNROLL
+        for (int po = 0; po < K2; ++po)
+            v = fmaf(T2s[(((po / 3) * 9 + f * 3 + g) * G::PO + po % 3) * G::S + s], Z.get(po), v);
+        valp[gf * G::S + s] = v;
+    }
+}
+
+// value, loss and d loss / d value of the tile's samples (MODE 0: values only)
+template <int R, int MODE>
+TNQ_HD void last_value(const Ctx& c, int tid) {
+    using G = Geo<R>;
+    if (tid >= G::S) return;
+    float* valp = c.sm + G::OFF_VAL;
+    float val = 0.f;
+    TNQ_UNROLL
+    for (int gf = 0; gf < K2; ++gf) val += valp[gf * G::S + tid];
+    const long long b = c.b0 + tid;
+    const bool valid = b < c.B;
+    if (MODE != 2 && valid && c.values != nullptr) c.values[b] = val;
+    float dv = 0.f, lo = 0.f;
+    if (MODE == 1) {
+        const float cl = val > 1e-10f ? val : 1e-10f;
+        if (valid) {
+            lo = -(logf(cl) + c.log_scale) * c.inv_count;
+            dv = val >= 1e-10f ? -c.inv_count / cl : 0.f;
+        }
+    } else if (MODE == 2) {
+        dv = valid ? ldg_f(c.seed + b) : 0.f;
+    }
+    valp[K2 * G::S + tid] = lo;
+    valp[K2 * G::S + G::S + tid] = dv;
+}
+
+// ================================= reverse phases ======================================================
+
+// reverse of the last step (task = (g,f,sample)): d T2 (complete), d X of both copies
+template <int R>
+TNQ_HD void last_bwd(const Ctx& c, TS& ts, int tid) {
+    using G = Geo<R>;
+    const int n = c.a->n;
+    const float* T2s = c.sm + G::OFF_T2;
+    float* dT2r = c.sm + G::OFF_DT2R;
+    float* rows = c.sm + G::OFF_FL;        // XL rows [(g,f,h,i)][sample]
+    const float* dval = c.sm + G::OFF_VAL + K2 * G::S + G::S;
+    TNQ_UNROLL
+    for (int x = 0; x < K2; ++x) ts.accX[x].zero();
+    TNQ_UNROLL
+    for (int x = 0; x < K2; ++x) ts.accB[x].zero();
+    const int tail = (n - 1) * C_STEP;
+    TNQ_NOUNROLL
+    for (int t = tid; t < K2 * G::S; t += NT) {
+        const int gf = t / G::S, s = t % G::S, g = gf / 3, f = gf % 3;
+        float mh[K][K], mi[K][K], L[K][K];
+        Vec<K2> Z;
+        last_lz<R>(c, gf, s, mh, mi, L, Z);
+        const float dv = dval[s];
+        Vec<K2> Lv, dL;
+        TNQ_UNROLL
+        for (int jp = 0; jp < K2; ++jp) Lv.set(jp, L[jp / 3][jp % 3]);
+        dL.zero();
+        TNQ_UNROLL
+        for (int po = 0; po < K2; ++po) {
+            const int p0 = po / 3, o = po % 3;
+            const float dz = dv * T2s[((p0 * 9 + f * 3 + g) * G::PO + o) * G::S + s];
+            dT2r[((o * 9 + f * 3 + g) * G::PO + p0) * G::S + s] = dv * Z.get(po);
+            axpy(ts.accX[po], dz, Lv);                          // d X[p0,o,j,p'] (right copy)
+            Vec<K2> xn;
+            cvec<K2>(c, xn, tail + T_XN + po * 10);             // X[p0,o,j,p'] over (j,p')
+            axpy(dL, dz, xn);
+        }
+        float dtmp[K][K];                  // [h][p'] = sum_j Mh[h][j] dL[j][p']
+        TNQ_UNROLL
+        for (int h = 0; h < K; ++h)
+            TNQ_UNROLL
+            for (int pp = 0; pp < K; ++pp) {
+                float v = 0.f;
+                TNQ_UNROLL
+                for (int j = 0; j < K; ++j) v = fmaf(mh[h][j], dL.get(j * 3 + pp), v);
+                dtmp[h][pp] = v;
+            }
+        TNQ_UNROLL
+        for (int h = 0; h < K; ++h)
+            TNQ_UNROLL
+            for (int i = 0; i < K; ++i) {
+                float v = 0.f;
+                TNQ_UNROLL
+                for (int pp = 0; pp < K; ++pp) v = fmaf(dtmp[h][pp], mi[i][pp], v);
+                rows[(gf * K2 + h * 3 + i) * G::SP + s] = v;     // d X[g,f,h,i] (left copy), this sample
+            }
+    }
+}
+
+// flush scratch of warp `warp`: rows [27*ROUND, 27*ROUND+27) of this lane's accumulators
+template <int R, int ROUND>
+TNQ_HD void flush_put(const Ctx& c, const TS& ts, int warp, int lane) {
+    using G = Geo<R>;
+    float* buf = c.sm + G::OFF_FL + warp * (K3 * 33);
+    TNQ_UNROLL
+    for (int r = 0; r < K3; ++r) {
+        if (ROUND < 3) buf[r * 33 + lane] = ts.accX[(ROUND * K3 + r) / K2].get((ROUND * K3 + r) % K2);
+        else buf[r * 33 + lane] = ts.accB[r / 3].get(r % 3);
+    }
+}
+template <int R>
+TNQ_HD void flush_sum(const Ctx& c, int round, int warp, int lane) {
+    using G = Geo<R>;
+    if (lane >= K3) return;
+    const float* buf = c.sm + G::OFF_FL + warp * (K3 * 33) + lane * 33;
+    float t = 0.f;
+    TNQ_UNROLL
+    for (int l = 0; l < 32; ++l) t += buf[l];
+    c.sm[G::OFF_WS + warp * 108 + round * K3 + lane] = t;
+}
+
+// which o each (thread group, flush slot) of the d T2 partial sums holds: computed once per CTA
+template <int R>
+TNQ_HD void build_sources(const Ctx& c, int tid) {
+    using G = Geo<R>;
+    int* src = reinterpret_cast<int*>(c.sm + G::OFF_SRC);       // [3][64] lists | [3] counts | ...
+    if (tid != 0) return;
+    int cnt[3] = {0, 0, 0};
+    for (int w = 0; w < NW; ++w)
+        for (int slot = 0; slot < R; ++slot) {
+            int cur = -1, fs = 0;
+            for (int u = ustart<R>(w); u < ustart<R>(w + 1); ++u) {
+                const int id = rb_of<R>(u, slot);
+                if (id < 0) continue;
+                const int o = id / 9;
+                if (o != cur) {
+                    if (cur >= 0) ++fs;
+                    cur = o;
+                    src[o * 64 + cnt[o]++] = fs * NT + w * 32 + slot * G::S;    // flush slot, first thread of the group
+                }
+            }
+        }
+    for (int o = 0; o < 3; ++o) src[3 * 64 + o] = cnt[o];
+}
+
+// reverse of the fused phase (row block (o,q',r)): from d T1_{q+1}, d T2_{q+1}, T2_q, U_q
+//   E' (recomputed), d Bs_{q+1} (both parts), d E', d X_q (left copy), d V, d T2_q and d U_q partial sums
+template <int R>
+TNQ_HD void phase_r(const Ctx& c, TS& ts, int q, int warp, int lane) {
+    using G = Geo<R>;
+    const float* dT1s = c.sm + G::OFF_T1;
+    const float* dT2r = c.sm + G::OFF_DT2R;
+    float* dT2p = c.sm + G::OFF_DT2P;
+    float* dUp = c.sm + G::OFF_DUP;
+    float* p2p = c.sm + G::OFF_P2P;
+    const int cq = q * C_STEP, cq1 = (q + 1) * C_STEP;
+    const int s = lane % G::S, tid = warp * 32 + lane;
+    TNQ_UNROLL
+    for (int x = 0; x < K2; ++x) ts.accX[x].zero();
+    TNQ_UNROLL
+    for (int x = 0; x < K2; ++x) ts.accB[x].zero();
+    Vec<K2> dT2acc[K];                     // [p'] over (f,g')
+    TNQ_UNROLL
+    for (int p = 0; p < K; ++p) dT2acc[p].zero();
+    int cur_o = -1, fs = 0;
+    TNQ_NOUNROLL
+    for (int u = ustart<R>(warp); u < ustart<R>(warp + 1); ++u) {
+        RowBlock<R> rb;
+        if (!row_block<R>(c, u, lane, rb)) continue;
+        if (rb.o != cur_o) {                // the running d T2 sum belongs to another o: park it
+            if (cur_o >= 0) {
+                TNQ_UNROLL
+                for (int x = 0; x < K3; ++x) dT2p[(x * 2 + fs) * NT + tid] = dT2acc[x / 9].get(x % 9);
+                TNQ_UNROLL
+                for (int p = 0; p < K; ++p) dT2acc[p].zero();
+                ++fs;
+            }
+            cur_o = rb.o;
+        }
+        float u9[K2];
+        TNQ_UNROLL
+        for (int x = 0; x < K2; ++x) u9[x] = rb.uu[x * G::PQ * G::S];
+        Vec<K> d1[K];                      // d T1_{q+1}: [j] over f''
+        TNQ_UNROLL
+        for (int j = 0; j < K; ++j)
+            TNQ_UNROLL
+            for (int f2 = 0; f2 < K; ++f2) d1[j].set(f2, dT1s[((f2 * 3 + j) * G::NU + u) * 32 + lane]);
+        Vec<K2> V[K];
+        make_v<R>(rb, u9, V);
+        {   // E' -> d Bs part 1, T1 (recomputed) -> d Bs part 2
+            Vec<K2> E[K];
+            make_e(c, cq, V, E);
+            Vec<K> T1c[K];                 // [j] over f''
+            TNQ_UNROLL
+            for (int j = 0; j < K; ++j) T1c[j].zero();
+            TNQ_UNROLL
+            for (int fh = 0; fh < K2; ++fh) {
+                Vec<K> b;
+                cvec<K>(c, b, cq1 + C_BA + fh * 4);
+                TNQ_UNROLL
+                for (int j = 0; j < K; ++j) {
+                    const float e = E[fh / 3].get((fh % 3) * 3 + j);
+                    axpy(ts.accB[fh], e, d1[j]);
+                    axpy(T1c[j], e, b);
+                }
+            }
+            const int r = rb.qr % 3;
+            TNQ_UNROLL
+            for (int o2 = 0; o2 < K; ++o2) {
+                float acc = 0.f;
+                TNQ_UNROLL
+                for (int f2 = 0; f2 < K; ++f2)
+                    TNQ_UNROLL
+                    for (int j = 0; j < K; ++j)
+                        acc = fmaf(T1c[j].get(f2), dT2r[((o2 * 9 + f2 * 3 + j) * G::PO + r) * G::S + s], acc);
+                p2p[(o2 * G::NU + u) * 32 + lane] = acc;
+            }
+        }
+        Vec<K2> dE[K];                     // [f] over (h,j) = sum_f'' Bs'[f,h,f''] d T1[f'',j]
+        TNQ_UNROLL
+        for (int fh = 0; fh < K2; ++fh) {
+            Vec<K> b;
+            cvec<K>(c, b, cq1 + C_BA + fh * 4);
+            TNQ_UNROLL
+            for (int j = 0; j < K; ++j) dE[fh / 3].set((fh % 3) * 3 + j, dot(b, d1[j], 0.f));
+        }
+        TNQ_UNROLL
+        for (int g = 0; g < K; ++g)
+            TNQ_UNROLL
+            for (int i = 0; i < K; ++i)
+                TNQ_UNROLL
+                for (int f = 0; f < K; ++f) axpy(ts.accX[g * 3 + i], V[i].get(f * 3 + g), dE[f]);
+        Vec<K2> W[K];                      // d V: [i'] over (f,g')
+        {
+            Vec<K2> dV[K];                 // [f] over (g',i') = sum_(h,j) d E'[f][(h,j)] X[g',h,i',j]
+            TNQ_UNROLL
+            for (int f = 0; f < K; ++f) dV[f].zero();
+            TNQ_UNROLL
+            for (int hj = 0; hj < K2; ++hj) {
+                Vec<K2> xb;
+                cvec<K2>(c, xb, cq + C_XB + hj * 10);
+                TNQ_UNROLL
+                for (int f = 0; f < K; ++f) axpy(dV[f], dE[f].get(hj), xb);
+            }
+            TNQ_UNROLL
+            for (int i = 0; i < K; ++i)
+                TNQ_UNROLL
+                for (int fg = 0; fg < K2; ++fg) W[i].set(fg, dV[fg / 3].get((fg % 3) * 3 + i));
+        }
+        TNQ_UNROLL
+        for (int p = 0; p < K; ++p) {
+            TNQ_UNROLL
+            for (int i = 0; i < K; ++i) axpy(dT2acc[p], u9[i * 3 + p], W[i]);
+            Vec<K2> t;
+            TNQ_UNROLL
+            for (int fg = 0; fg < K2; ++fg) t.set(fg, rb.t2[(p * 9 + fg) * G::PO * G::S]);
+            TNQ_UNROLL
+            for (int i = 0; i < K; ++i) dUp[((i * 3 + p) * G::NU + u) * 32 + lane] = dot(W[i], t, 0.f);
+        }
+    }
+    if (cur_o >= 0) {
+        TNQ_UNROLL
+        for (int x = 0; x < K3; ++x) dT2p[(x * 2 + fs) * NT + tid] = dT2acc[x / 9].get(x % 9);
+    }
+}
+
+// S.a: everything that only needs sums over partial results of phase_r
+//   left: true  -> rows 0..80 of the flushed accumulators are d X (left copy) in (g',i',h,j) order  (phase_r)
+//         false -> they are d X (right copy) in natural order (reverse of the last step)
+template <int R>
+TNQ_HD void phase_sa(const Ctx& c, int q, bool after_r, int tid) {
+    using G = Geo<R>;
+    const float* ws = c.sm + G::OFF_WS;
+    float* gq = c.gpart + (long long)q * GQ;
+    if (tid < 108) {
+        float t = 0.f;
+        TNQ_UNROLL
+        for (int w = 0; w < NW; ++w) t += ws[w * 108 + tid];
+        if (!after_r) {
+            if (tid < K4) gq[K4 + tid] = t;
+        } else if (tid < K4) {
+            const int gi = tid / 9, hj = tid % 9;
+            gq[(((gi / 3) * 3 + hj / 3) * 3 + gi % 3) * 3 + hj % 3] = t;
+        } else {
+            gq[GQ + 162 + tid - K4] = t;                        // d Bs_{q+1} part 1, natural (c,e,f)
+        }
+    }
+    if (!after_r) return;
+    // d Bs_{q+1} part 2: [(l,n)][o''] = sum over p and the samples
+    if (tid < K3) {
+        const int ln = tid / 3, o2 = tid % 3;
+        const float* p2p = c.sm + G::OFF_P2P;
+        float t = 0.f;
+        for (int p = 0; p < K; ++p) {
+            int u, slot;
+            uslot_of<R>(ln * 3 + p, u, slot);
+            for (int s = 0; s < G::S; ++s) t += p2p[(o2 * G::NU + u) * 32 + slot * G::S + s];
+        }
+        gq[GQ + 189 + tid] = t;
+    }
+    // d T2_q = sum of the parked partial sums, stored where the next phase_r / phase_sb read it
+    {
+        const float* dT2p = c.sm + G::OFF_DT2P;
+        float* dT2r = c.sm + G::OFF_DT2R;
+        const int* src = reinterpret_cast<const int*>(c.sm + G::OFF_SRC);
+        TNQ_NOUNROLL
+        for (int t = tid; t < K4 * G::S; t += NT) {
+            const int s = t % G::S, e = t / G::S;              // e = x*3 + o, x = p'*9 + f*3 + g'
+            const int o = e % 3, x = e / 3, p = x / 9, fg = x % 9;
+            const int cnt = src[3 * 64 + o];
+            float v = 0.f;
+            for (int k = 0; k < cnt; ++k) {
+                const int w = src[o * 64 + k];
+                v += dT2p[(x * 2 + w / NT) * NT + (w % NT) + s];
+            }
+            dT2r[((o * 9 + fg) * G::PO + p) * G::S + s] = v;
+        }
+    }
+    // d U_q = sum over o of the partial sums; right-copy d X_q[p',q',k,r] = sum_i' M_q[i',k] d U[i',p',q',r], per sample
+    {
+        const float* dUp = c.sm + G::OFF_DUP;
+        const float* MA = c.sm + G::OFF_MA;
+        float* rows = c.sm + G::OFF_FL;
+        TNQ_NOUNROLL
+        for (int t = tid; t < K3 * G::S; t += NT) {
+            const int s = t % G::S, e = t / G::S;              // e = p'*9 + qr
+            const int p = e / 9, qr = e % 9;
+            float du[K];
+            TNQ_UNROLL
+            for (int i = 0; i < K; ++i) {
+                float v = 0.f;
+                TNQ_UNROLL
+                for (int o = 0; o < K; ++o) {
+                    int u, slot;
+                    uslot_of<R>(o * 9 + qr, u, slot);
+                    v += dUp[((i * 3 + p) * G::NU + u) * 32 + slot * G::S + s];
+                }
+                du[i] = v;
+            }
+            TNQ_UNROLL
+            for (int k = 0; k < K; ++k) {
+                float v = 0.f;
+                TNQ_UNROLL
+                for (int i = 0; i < K; ++i) v = fmaf(MA[(i * 3 + k) * G::S + s], du[i], v);
+                rows[(((p * 3 + qr / 3) * 3 + k) * 3 + qr % 3) * G::SP + s] = v;
+            }
+        }
+    }
+}
+
+// sum of the per-sample rows [81][SP] over the samples -> gradient slice
+template <int R>
+TNQ_HD void rows_to_grad(const Ctx& c, float* dst, int row0, int nrows, int tid) {
+    using G = Geo<R>;
+    if (tid >= nrows) return;
+    const float* rows = c.sm + G::OFF_FL + (row0 + tid) * G::SP;
+    float t = 0.f;
+    for (int s = 0; s < G::S; ++s) t += rows[s];
+    dst[tid] = t;
+}
+
+// S.b: d T1_q = A2^T (d T2_q)  (task = (f,p,g,sample)); q = 0: d As0 per sample instead
+template <int R>
+TNQ_HD void phase_sb(const Ctx& c, int q, int tid) {
+    using G = Geo<R>;
+    const float* dT2r = c.sm + G::OFF_DT2R;
+    if (q == 0) {
+        // d As0[e][f'] = sum_{p,o} d T2[f',o,e,p] As0[p][o] + sum_{g,f} d T2[f,f',g,e] As0[g][f]
+        float* rows = c.sm + G::OFF_FL + K4 * G::SP;
+        const int base = (c.a->n - 1) * C_STEP + T_AS0;
+        TNQ_NOUNROLL
+        for (int t = tid; t < K2 * G::S; t += NT) {
+            const int s = t % G::S, ef = t / G::S, e = ef / 3, f1 = ef % 3;
+            float v = 0.f;
+            for (int a1 = 0; a1 < K; ++a1)
+                for (int b1 = 0; b1 < K; ++b1) {
+                    // first term: (p,o) = (a1,b1);  second term: (g,f) = (a1,b1)
+                    v = fmaf(dT2r[((b1 * 9 + f1 * 3 + e) * G::PO + a1) * G::S + s], TNQ2_CST(base + a1 * 3 + b1), v);
+                    v = fmaf(dT2r[((f1 * 9 + b1 * 3 + a1) * G::PO + e) * G::S + s], TNQ2_CST(base + a1 * 3 + b1), v);
+                }
+            rows[ef * G::SP + s] = v;
+        }
+        return;
+    }
+    float* dT1s = c.sm + G::OFF_T1;
+    const int cq = q * C_STEP;
+    TNQ_NOUNROLL
+    for (int t = tid; t < K3 * G::S; t += NT) {
+        const int s = t % G::S, x = t / G::S;
+        const int g = x % 3, p = (x / 3) % 3, f = x / 9;
+        Vec<K2> out;                       // over (l,n)
+        out.zero();
+        TNQ_UNROLL
+        for (int o = 0; o < K; ++o) {
+            Vec<K2> bb;
+            cvec<K2>(c, bb, cq + C_BB + o * 10);
+            axpy(out, dT2r[((o * 9 + f * 3 + g) * G::PO + p) * G::S + s], bb);
+        }
+        TNQ_UNROLL
+        for (int ln = 0; ln < K2; ++ln) {
+            int u, slot;
+            uslot_of<R>(ln * 3 + p, u, slot);
+            dT1s[((f * 3 + g) * G::NU + u) * 32 + slot * G::S + s] = out.get(ln);
+        }
+    }
+}
+
+// S.c: operands of phase_r(q): T2_q (checkpoint, or As0 (x) As0 for q = 0), U_q, M_q
+template <int R>
+TNQ_HD void phase_sc(const Ctx& c, int q, int tid) {
+    using G = Geo<R>;
+    if (q == 0) {
+        fill_t2_first<R>(c, tid);
+    } else {
+        float* T2s = c.sm + G::OFF_T2;
+        const float* ck = c.ck + (long long)(q - 1) * G::T2_SZ;
+        for (int e = tid; e < G::T2_SZ; e += NT) T2s[e] = ck[e];
+    }
+    phase_u<R>(c, q, tid);
+    load_ms<R>(c, q, c.sm + G::OFF_MA, tid);
+}
+
+}  // namespace tnq_l2
+
+// -------------------------------------------------------------------------------------------------------
+// The sweep of one tile.  TNQ2_PH(body) runs `body` for every thread of the CTA and then makes the
+// shared-memory writes visible to the whole CTA (device: __syncthreads(); CPU emulation: a loop over
+// the 128 threads); TNQ2_PHW is the same with warp scope (device: __syncwarp()).
+// -------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+#define TNQ2_PH(...)  \
+    { __VA_ARGS__ }   \
+    __syncthreads();
+#define TNQ2_PHW(...) \
+    { __VA_ARGS__ }   \
+    __syncwarp();
+#define TNQ2_THREAD_PARAM TS &ts, const int tid
+#else
+#define TNQ2_PH(...)                        \
+    for (int tid = 0; tid < NT; ++tid) {    \
+        TS& ts = tss[tid];                  \
+        (void)ts;                           \
+        __VA_ARGS__                         \
+    }
+#define TNQ2_PHW(...) TNQ2_PH(__VA_ARGS__)
+#define TNQ2_THREAD_PARAM TS* tss
+#endif
+
+namespace tnq_l2 {
+
+// MODE 0: values.  MODE 1: values + fused loss + gradients.  MODE 2: gradients seeded by c.seed.
+template <int R, int MODE>
+TNQ_HD void tile_sweep(const Ctx& c, TNQ2_THREAD_PARAM) {
+    using G = Geo<R>;
+    const int n = c.a->n;
+    constexpr bool CK = MODE != 0;
+#define TNQ2_WARP (tid >> 5)
+#define TNQ2_LANE (tid & 31)
+    // ------------------------------- forward sweep -------------------------------
+    TNQ2_PH(fill_t2_first<R>(c, tid); phase_u<R>(c, 0, tid);)
+    for (int q = 0; q <= n - 3; ++q) {
+        TNQ2_PH(phase_c_a1<R>(c, q, TNQ2_WARP, TNQ2_LANE);)
+        TNQ2_PH(
+            phase_a2<R, CK>(c, q + 1, tid);
+            if (q + 1 <= n - 3) {
+                phase_u<R>(c, q + 1, tid);
+            } else {
+                load_ms<R>(c, n - 2, c.sm + G::OFF_MA, tid);
+                load_ms<R>(c, n - 1, c.sm + G::OFF_MB, tid);
+            })
+    }
+    TNQ2_PH(last_fwd<R>(c, tid);)
+    TNQ2_PH(last_value<R, MODE>(c, tid);)
+    if (MODE == 0) return;
+    // ------------------------------- reverse sweep -------------------------------
+    TNQ2_PH(
+        if (MODE == 1 && tid == 0) {
+            float t = 0.f;
+            for (int s = 0; s < G::S; ++s) t += c.sm[G::OFF_VAL + K2 * G::S + s];
+            *c.lpart = t;
+        }
+        last_bwd<R>(c, ts, tid);)
+    TNQ2_PH(rows_to_grad<R>(c, c.gpart + (long long)(n - 2) * GQ, 0, K4, tid);)
+#define TNQ2_FLUSH(ROUND)                                                  \
+    TNQ2_PHW(flush_put<R, ROUND>(c, ts, TNQ2_WARP, TNQ2_LANE);)             \
+    TNQ2_PHW(flush_sum<R>(c, ROUND, TNQ2_WARP, TNQ2_LANE);)
+    TNQ2_FLUSH(0)
+    TNQ2_FLUSH(1)
+    TNQ2_FLUSH(2)
+    TNQ2_PH()
+    TNQ2_PH(phase_sa<R>(c, n - 2, false, tid); phase_sb<R>(c, n - 2, tid);)
+    for (int q = n - 3; q >= 0; --q) {
+        TNQ2_PH(phase_sc<R>(c, q, tid);)
+        TNQ2_PH(phase_r<R>(c, ts, q, TNQ2_WARP, TNQ2_LANE);)
+        TNQ2_FLUSH(0)
+        TNQ2_FLUSH(1)
+        TNQ2_FLUSH(2)
+        TNQ2_FLUSH(3)
+        TNQ2_PH()
+        TNQ2_PH(phase_sa<R>(c, q, true, tid);)
+        TNQ2_PH(rows_to_grad<R>(c, c.gpart + (long long)q * GQ + K4, 0, K4, tid); phase_sb<R>(c, q, tid);)
+    }
+    TNQ2_PH(rows_to_grad<R>(c, c.gpart + 162, K4, K2, tid);)
+#undef TNQ2_FLUSH
+#undef TNQ2_WARP
+#undef TNQ2_LANE
+}
+
+// Finalize: element v of the gradient of core A_q (layer 0) or X_q (layer 1), summed over the tiles
+// [t0, t1) in tile order, with the circuit states folded back in for layer 0 (the caller combines the
+// chunks in a fixed order):  dA_q[c,d,e,f] = dBs_q[c,e,f] s_{q+1}[d] (q >= 1), dA_0 = dAs0[e,f] s_0[c] s_1[d]
+TNQ_HD float grad_chunk(const Args& a, const float* gparts, long long t0, long long t1, int layer, int q, int v) {
+    const int n = a.n;
+    const long long stride = grad_floats(n);
+    float t = 0.f;
+    if (layer == 1) {
+        const float* g = gparts + (long long)q * GQ + v;
+        for (long long i = t0; i < t1; ++i) t += g[i * stride] + g[i * stride + K4];
+        return t;
+    }
+    const int f = v % K, e = (v / K) % K, d = (v / K2) % K, cc = v / K3;
+    if (q == 0) {
+        const float* g = gparts + 162 + e * K + f;
+        for (long long i = t0; i < t1; ++i) t += g[i * stride];
+        return t * a.state[0][cc] * a.state[1][d];
+    }
+    const float* g = gparts + (long long)q * GQ + 162 + (cc * K + e) * K + f;
+    for (long long i = t0; i < t1; ++i) t += g[i * stride] + g[i * stride + K3];
+    return t * a.state[q + 1][d];
+}
+
+}  // namespace tnq_l2

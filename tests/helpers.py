@@ -5,6 +5,14 @@ import torch
 from oracle import qctn_oracle as oc
 
 
+# Two float32 implementations that sum in different orders carry INDEPENDENT rounding noise; where a
+# batch amplifies it (1/p weights of samples that partly cancel) the ratio of their errors against
+# float64 fluctuates by several x in either direction (measured 0.2 .. 5.3 on seeded batches, see
+# DESIGN.md "Parity").  The CUDA path is therefore required to be within 1e-5, or within NOISE_FACTOR x
+# the reference's own float32 error on the same batch, whichever is larger.
+NOISE_FACTOR = 8
+
+
 def make_case(graph, K, B, dtype, tnt=True, mode="a", seed=0, identity_q=()):
     """Seeded CPU inputs for one contraction: cores, unit states, measurement matrices."""
     torch.manual_seed(seed)
@@ -62,7 +70,23 @@ def well_conditioned_case(graph, K, B, dtype, seed=0, keep=0.05, mode="a"):
     survivors = torch.nonzero(p >= keep * p.median()).flatten()
     assert len(survivors) >= B, "not enough well-conditioned samples"
     gen = torch.Generator().manual_seed(1000 + seed)
-    good = survivors[torch.randperm(len(survivors), generator=gen)[:B]].sort().values
+    order = survivors[torch.randperm(len(survivors), generator=gen)]
+    good = order[:B].sort().values
+    for _ in range(4):
+        # the loss clamps the SCALED value at 1e-10 (engine_siamese.py:490-530): a sample within 5 % of
+        # the clamp flips between "gradient dp/p" and "gradient 0" on the last float32 bit -- swap those
+        # for other survivors (the TNTensor scales depend on the selected batch, hence the loop)
+        mxs, _ = oc.generate_data(x[good], K, td, "TNTensor")
+        scale = 1.0
+        for m in mxs:
+            scale *= m.scale
+        ps = p[good] / (scale ** 2 if td.is_complex else scale)
+        near = (ps / 1e-10).log().abs() < 0.05
+        if not near.any():
+            break
+        pool = [int(i) for i in order if int(i) not in set(good.tolist())]
+        keepers = good[~near].tolist()
+        good = torch.tensor(sorted(keepers + pool[:B - len(keepers)]))
     mxs, _ = oc.generate_data(x[good], K, td, "TNTensor")
     if mode == "ab":
         eye = torch.eye(K, dtype=td).expand(B, K, K)

@@ -9,7 +9,7 @@ import torch
 
 import tneq_b200
 from oracle import qctn_oracle as oc
-from helpers import well_conditioned_case, upcast, clone_mx, rel_err
+from helpers import well_conditioned_case, upcast, clone_mx, rel_err, NOISE_FACTOR
 
 pytestmark = pytest.mark.gpu
 H = tneq_b200.QCTNHelper
@@ -55,7 +55,7 @@ def test_gemm_path_matches_oracle(kind, n, K, B, dtype, built_lib, force_gemm_pa
     # complex dtypes return |amplitude|^2 (reference quirk D10): the amplitude's 1e-5 bound doubles
     truth = oc.forward(graph, c64, s64, [upcast(m, td64) for m in clone_mx(mxs)])
     tol_p = 2e-5 if "complex" in dtype else 1e-5
-    assert rel_err(got.double(), truth) < max(tol_p, 3 * rel_err(want.double(), truth))
+    assert rel_err(got.double(), truth) < max(tol_p, NOISE_FACTOR * rel_err(want.double(), truth))
     for fused in (True, False):
         loss, grads = eng.contract_with_compiled_strategy_for_gradient(
             q, st, [_to_dev(m, dev) for m in clone_mx(mxs)], fused=fused)
@@ -63,33 +63,122 @@ def test_gemm_path_matches_oracle(kind, n, K, B, dtype, built_lib, force_gemm_pa
         for g_, w, t in zip(grads, wg, tg):
             assert g_.shape == w.shape and g_.dtype == w.dtype
             ref_err = rel_err(w.to(td64), t)
-            assert rel_err(g_.to(td64), t) < max(1e-5, 3 * ref_err), (fused, rel_err(g_.to(td64), t), ref_err)
+            assert rel_err(g_.to(td64), t) < max(1e-5, NOISE_FACTOR * ref_err), (fused, rel_err(g_.to(td64), t), ref_err)
 
 
-def test_large_bond_normalisation(built_lib):
-    """KAT-1 at a bond dimension the CPU oracle cannot reach (32, complex64): unitary cores (QR in
-    complex128, then cast) + identity measurements => value 1 for every sample.
-    Tolerance 5e-5, not 1e-5: the tensor core adds into its fp32 accumulator with truncation, which
-    leaves a systematic bias of roughly -1e-6 per GEMM in the chain even with the split-accumulator
-    scheme of tnq_gemm.cu (measured -3.2e-5 here, -6.7e-6 at bond 16); DESIGN.md section 4."""
-    K, n, B = 32, 6, 3
+def _unitary_cores(q, K, dtype=torch.complex64, seed=0):
+    torch.manual_seed(seed)
+    for c in q.cores:
+        m = torch.randn(K * K, K * K, dtype=torch.complex128, device="cuda")
+        qm, _ = torch.linalg.qr(m)
+        q.cores_weights[c] = qm.reshape(K, K, K, K).to(dtype)
+        del m, qm
+
+
+def _last_states(K, n, dtype=torch.complex64):
+    st = [torch.zeros(K, dtype=dtype, device="cuda") for _ in range(n)]
+    for s in st:
+        s[-1] = 1.0
+    return st
+
+
+@pytest.mark.parametrize("K,n,B", [(32, 6, 3), (64, 6, 3), (64, 16, 2), (128, 4, 2)])
+def test_large_bond_normalisation(K, n, B, built_lib):
+    """KAT-1 at bond dimensions the CPU oracle cannot reach (32, 64 -- also at BASELINE cfg4's 16
+    qubits -- and 128, complex64): unitary cores (QR in complex128, then cast) + identity
+    measurements => value 1 for every sample, to the north-star tolerance of 1e-5.
+    The tensor core adds into its fp32 accumulator with truncation; tnq_gemm.cu drains the
+    accumulator after every k-block and sums the partial results round-to-nearest (its header)."""
     graph = H.generate_example_graph(n=n, graph_type="mps", dim_char=str(K))
     be = tneq_b200.BackendFactory.create_backend("b200", device="cuda:0", dtype="complex64")
     eng = tneq_b200.EngineSiamese(backend=be, strategy_mode="balanced", mx_K=K)
     q = tneq_b200.QCTN(graph)
-    torch.manual_seed(0)
-    for c in q.cores:
-        m = torch.randn(K * K, K * K, dtype=torch.complex128, device="cuda")
-        qm, _ = torch.linalg.qr(m)
-        q.cores_weights[c] = qm.reshape(K, K, K, K).to(torch.complex64)
-    st = [torch.zeros(K, dtype=torch.complex64, device="cuda") for _ in range(n)]
-    for s in st:
-        s[-1] = 1.0
+    _unitary_cores(q, K)
+    st = _last_states(K, n)
     eye = torch.eye(K, dtype=torch.complex64, device="cuda").expand(B, K, K)
     got = eng.contract_with_compiled_strategy(q, st, [eye] * n)
     fn = eng._compiled(q, st, [eye] * n, True, "symmetric")
     assert next(iter(fn.plans.values())).use_gemm_path
-    assert torch.allclose(got.cpu(), torch.ones(B), atol=5e-5), got
+    assert torch.allclose(got.cpu(), torch.ones(B), atol=1e-5), got
+
+
+@pytest.mark.parametrize("K,n,B", [(64, 5, 4), (128, 3, 2)])
+def test_large_bond_identity_circuit(K, n, B, built_lib):
+    """KAT-2 at bond 64 / 128: identity cores, states e_{K-1} => amplitude = prod_q M_q[b, K-1, K-1]
+    (complex dtypes report |amplitude|^2, reference quirk D10)."""
+    graph = H.generate_example_graph(n=n, graph_type="mps", dim_char=str(K))
+    be = tneq_b200.BackendFactory.create_backend("b200", device="cuda:0", dtype="complex64")
+    eng = tneq_b200.EngineSiamese(backend=be, strategy_mode="balanced", mx_K=K)
+    q = tneq_b200.QCTN(graph)
+    ident = torch.eye(K * K, dtype=torch.complex64, device="cuda").reshape(K, K, K, K)
+    for c in q.cores:
+        q.cores_weights[c] = ident
+    st = _last_states(K, n)
+    torch.manual_seed(1)
+    mx = []
+    for _ in range(n):
+        h = torch.randn(B, K, K, dtype=torch.complex64, device="cuda") / (2.0 * K ** 0.5)
+        mx.append(torch.eye(K, dtype=torch.complex64, device="cuda") + 0.3 * (h + h.transpose(1, 2).conj()))
+    got = eng.contract_with_compiled_strategy(q, st, mx)
+    amp = torch.ones(B, dtype=torch.complex128, device="cuda")
+    for m in mx:
+        amp = amp * m[:, K - 1, K - 1].to(torch.complex128)
+    want = (amp.real ** 2 + amp.imag ** 2).cpu()
+    assert rel_err(got.double().cpu(), want) < 2e-5      # |amplitude|^2: the amplitude's 1e-5 doubles
+
+
+def _mps_f64(cores, states, mxs):
+    """The single-layer MPS sweep (einsum strings 'cdef,c,aeg,higj,h,d,i->ajf', 'cdef,aeg,higj,ahc,d,i->ajf',
+    'acd,adc->a') in complex128 on the GPU, pairwise in the plan compiler's own order (3 K^4 per
+    qubit and sample): the yardstick where the CPU oracle's K^6 intermediates are out of reach."""
+    n = len(states)
+    a0, ac = cores[0], cores[0].conj()
+    v = torch.einsum("cdef,c,d->ef", a0, states[0], states[1])
+    w = torch.einsum("higj,h,i->gj", ac, states[0], states[1])
+    env = torch.einsum("ef,aeg,gj->ajf", v, mxs[0], w)
+    for qd in range(1, n - 1):
+        a = cores[qd]
+        v = torch.einsum("cdef,d->cef", a, states[qd + 1])
+        w = torch.einsum("higj,i->hgj", a.conj(), states[qd + 1])
+        t1 = torch.einsum("ahc,cef->ahef", env, v)
+        t2 = torch.einsum("ahef,aeg->ahgf", t1, mxs[qd])
+        env = torch.einsum("ahgf,hgj->ajf", t2, w)
+    return torch.einsum("acd,adc->a", env, mxs[n - 1])
+
+
+@pytest.mark.parametrize("K,n,B", [(32, 6, 6), (64, 5, 4)])
+def test_large_bond_loss_and_gradients_vs_float64(K, n, B, built_lib):
+    """Values, loss and core gradients at bond 32 / 64 against a complex128 contraction of the same
+    network on the GPU (torch.autograd for the gradients): 1e-5 relative, gradients per tensor
+    relative to the largest entry."""
+    graph = H.generate_example_graph(n=n, graph_type="mps", dim_char=str(K))
+    be = tneq_b200.BackendFactory.create_backend("b200", device="cuda:0", dtype="complex64")
+    eng = tneq_b200.EngineSiamese(backend=be, strategy_mode="balanced", mx_K=K)
+    q = tneq_b200.QCTN(graph)
+    _unitary_cores(q, K, seed=3)
+    for c in q.cores:
+        q.cores_weights[c].requires_grad_(True)
+    st = _last_states(K, n)
+    torch.manual_seed(4)
+    mx = []
+    for _ in range(n):                      # I + 0.1 H: keeps the value O(1) (a random unitary's overlap is ~K^-n)
+        h = torch.randn(B, K, K, dtype=torch.complex64, device="cuda") / (2.0 * K ** 0.5)
+        mx.append(torch.eye(K, dtype=torch.complex64, device="cuda") + 0.1 * (h + h.transpose(1, 2).conj()))
+    got = eng.contract_with_compiled_strategy(q, st, mx)
+    loss, grads = eng.contract_with_compiled_strategy_for_gradient(q, st, mx)
+    fn = eng._compiled(q, st, mx, True, "symmetric")
+    assert next(iter(fn.plans.values())).use_gemm_path
+    c128 = [q.cores_weights[c].detach().to(torch.complex128).requires_grad_(True) for c in q.cores]
+    amp = _mps_f64(c128, [s.to(torch.complex128) for s in st], [m.to(torch.complex128) for m in mx])
+    val = amp.real ** 2 + amp.imag ** 2
+    assert rel_err(got.double().cpu(), val.detach().cpu()) < 2e-5
+    want_loss = -(torch.log(torch.clamp(val, min=1e-10))).mean()
+    want_grads = torch.autograd.grad(want_loss, c128)
+    # loss = -mean(log value): its ABSOLUTE error is the relative error of the values
+    assert abs(loss.item() - want_loss.item()) <= 1e-5 * max(abs(want_loss.item()), 1.0)
+    for g, w in zip(grads, want_grads):
+        assert g.shape == w.shape
+        assert rel_err(g.to(torch.complex128).cpu(), w.cpu()) < 1e-5, rel_err(g.to(torch.complex128).cpu(), w.cpu())
 
 
 def test_permute_kernel_paths(built_lib):

@@ -11,7 +11,7 @@ import torch
 
 import tneq_b200
 from oracle import qctn_oracle as oc
-from helpers import make_case, well_conditioned_case, upcast, clone_mx, rel_err, elem_rel_err
+from helpers import make_case, well_conditioned_case, upcast, clone_mx, rel_err, elem_rel_err, NOISE_FACTOR
 
 pytestmark = pytest.mark.gpu
 H = tneq_b200.QCTNHelper
@@ -34,7 +34,8 @@ def _setup(graph, K, cores):
     eng = tneq_b200.EngineSiamese(backend=be, strategy_mode="balanced", mx_K=K)
     q = tneq_b200.QCTN(graph, backend=be)
     for k, v in cores.items():
-        q.cores_weights[k] = v.to(DEV).requires_grad_(True)
+        # contiguous: a CUDA graph is only captured over the caller's own buffers (no hidden copies)
+        q.cores_weights[k] = v.to(DEV).contiguous().requires_grad_(True)
     return eng, q
 
 
@@ -55,17 +56,17 @@ def test_ladder_vs_oracle(n, K, B, built_lib):
     got = eng.contract_with_compiled_strategy(q, st, [_to_dev(m) for m in clone_mx(mxs)])
     assert _bound(eng, q, st, [_to_dev(m) for m in clone_mx(mxs)]).ladder is not None
     assert got.shape == want.shape and got.dtype == want.dtype
-    assert elem_rel_err(got.double(), truth) < max(1e-5, 3 * elem_rel_err(want.double(), truth))
+    assert elem_rel_err(got.double(), truth) < max(1e-5, NOISE_FACTOR * elem_rel_err(want.double(), truth))
     wl, wg = oc.loss_and_grads(graph, cores, states, clone_mx(mxs))
     tl, tg = oc.loss_and_grads(graph, c64, s64, [upcast(m, torch.float64) for m in clone_mx(mxs)])
     for fused in (True, False):   # fused loss kernel (mode 1), then the torch.autograd route (modes 0 + 2)
         loss, grads = eng.contract_with_compiled_strategy_for_gradient(q, st, [_to_dev(m) for m in clone_mx(mxs)],
                                                                        fused=fused)
-        assert abs(loss.item() - tl.item()) <= max(1e-5 * abs(tl.item()), 3 * abs(wl.item() - tl.item()))
+        assert abs(loss.item() - tl.item()) <= max(1e-5 * abs(tl.item()), NOISE_FACTOR * abs(wl.item() - tl.item()))
         assert len(grads) == len(wg)
         for g, w, t in zip(grads, wg, tg):
             assert g.shape == w.shape and g.dtype == w.dtype
-            assert rel_err(g.double(), t) < max(1e-5, 3 * rel_err(w.double(), t)), fused
+            assert rel_err(g.double(), t) < max(1e-5, NOISE_FACTOR * rel_err(w.double(), t)), fused
 
 
 def test_ladder_vs_vm_route(built_lib):
@@ -165,7 +166,7 @@ def test_cfg3_full_size_properties(built_lib):
                        [m.double() for m in sub])
     got = full[pick.to(DEV)].cpu()
     assert rel_err(got, want) < 1e-5
-    assert rel_err(got.double(), truth) < max(1e-5, 3 * rel_err(want.double(), truth))
+    assert rel_err(got.double(), truth) < max(1e-5, NOISE_FACTOR * rel_err(want.double(), truth))
     cut = 7001
     a = eng.contract_with_compiled_strategy(q, states, [m[:cut] for m in mx])
     b = eng.contract_with_compiled_strategy(q, states, [m[cut:] for m in mx])

@@ -16,7 +16,7 @@ import pytest
 import torch
 
 from oracle import qctn_oracle as oc
-from helpers import well_conditioned_case, clone_mx, rel_err
+from helpers import well_conditioned_case, clone_mx, rel_err, NOISE_FACTOR
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -108,7 +108,7 @@ def test_reference_engine_on_b200_backend(ref, kind, n, K, B, dtype):
     for g, w, t in zip(gg, wg, tg):
         assert g.shape == w.shape and g.dtype == w.dtype and g.device.type == "cuda"
         ref_err = rel_err(w.to(td64), t)
-        assert rel_err(g.to(td64), t) < max(1e-5, 3 * ref_err), (rel_err(g.to(td64), t), ref_err)
+        assert rel_err(g.to(td64), t) < max(1e-5, NOISE_FACTOR * ref_err), (rel_err(g.to(td64), t), ref_err)
 
 
 def test_reference_optimizer_step_and_probabilities(ref):
