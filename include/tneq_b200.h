@@ -110,6 +110,21 @@ int tnq_mps_chain(int K, int n, const float* const* cores, const float* const* s
  * gradient slices; bounded by the number of resident warps, not by B).
  */
 int64_t tnq_mps_ladder_workspace_bytes(int K, int n, int64_t B, int mode);
+/*
+ * The same sweep, second generation (csrc/tnq_ladder2.cu, edge rank 3; tnq_mps_ladder dispatches K = 3 here):
+ * a lane is a sample, tiles of 32/R samples per 4-warp CTA (R = 1, 2, 4, 8 picked from B and the SM count),
+ * core tensors as uniform operands from constant memory, the rank-6 environment kept in registers (phase C of
+ * a step fused with phase A of the next), T2 the only per-sample state checkpointed to HBM, the environment
+ * re-derived in the reverse sweep.  Same arguments and modes as tnq_mps_ladder.  The constant pool is one
+ * per device: launches must be stream-ordered with each other (one stream, or events between streams).
+ *   tnq_mps_ladder2_geometry: out[5] = {R, samples per tile, tiles, CTAs, dynamic shared bytes} for (n, B, mode).
+ */
+int64_t tnq_mps_ladder2_workspace_bytes(int n, int64_t B, int mode);
+int tnq_mps_ladder2_geometry(int n, int64_t B, int mode, int64_t* out);
+int tnq_mps_ladder2(int n, const float* const* cores_a, const float* const* cores_x, const float* const* states,
+                    const float* const* mx, const int64_t* mx_stride, int64_t B, int mode, const float* seed,
+                    float* values, float* loss, float* const* grads_a, float* const* grads_x, double log_scale,
+                    void* workspace, int64_t workspace_bytes, void* stream);
 int tnq_mps_ladder(int K, int n, const float* const* cores_a, const float* const* cores_x,
                    const float* const* states, const float* const* mx, const int64_t* mx_stride, int64_t B, int mode,
                    const float* seed, float* values, float* loss, float* const* grads_a, float* const* grads_x,

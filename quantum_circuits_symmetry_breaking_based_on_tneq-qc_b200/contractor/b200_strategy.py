@@ -202,7 +202,7 @@ class _Call:
         return flat.reshape(lead + body)
 
     # ---- single-layer MPS route: register-resident chain kernel (csrc/tnq_chain.cu) -----------
-    def _chain(self, cores, mode, seed=None, log_scale=0.0):
+    def _chain(self, cores, mode, seed=None, log_scale=0.0, private_ws=False):
         import ctypes
         from ctypes import c_void_p, c_int64
         from .. import _lib
@@ -222,8 +222,12 @@ class _Call:
             ms.append(m)
             strides.append(0 if (m.shape[0] == 1 and self.B != 1) else st[0])
         ws_bytes = int(lib.tnq_mps_chain_workspace_bytes(K, n, self.B))
-        if self.bound._chain_ws is None or self.bound._chain_ws.numel() < ws_bytes:
-            self.bound._chain_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        if private_ws:                  # captured into a CUDA graph: the graph owns its scratch
+            ws = self._keep = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        else:
+            if self.bound._chain_ws is None or self.bound._chain_ws.numel() < ws_bytes:
+                self.bound._chain_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            ws = self.bound._chain_ws
         values = torch.empty(self.B, dtype=torch.float32, device=dev) if mode != 2 else None
         loss = torch.empty(1, dtype=torch.float32, device=dev) if mode == 1 else None
         grads = [torch.empty_like(c) for c in cs] if mode != 0 else []
@@ -234,7 +238,7 @@ class _Call:
                                          c_void_p(values.data_ptr()) if values is not None else None,
                                          c_void_p(loss.data_ptr()) if loss is not None else None,
                                          arr(grads) if grads else None, float(log_scale),
-                                         c_void_p(self.bound._chain_ws.data_ptr()), self.bound._chain_ws.numel(),
+                                         c_void_p(ws.data_ptr()), ws.numel(),
                                          c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         gmap = dict(zip(order, grads))
         return values, (loss[0] if loss is not None else None), [gmap[k] for k in self.core_keys] if grads else []
@@ -336,11 +340,11 @@ class _Call:
                          else gflat.reshape(c.shape))
         return grads, val[r.g.result]
 
-    def forward(self, cores):
+    def forward(self, cores, private_ws: bool = False):
         if self.bound.chain_rank:
-            return self._chain(cores, 0)[0]
+            return self._chain(cores, 0, private_ws=private_ws)[0]
         if self.bound.ladder:
-            return self._ladder(cores, 0)[0]
+            return self._ladder(cores, 0, private_ws=private_ws)[0]
         if self.bound.use_gemm_path:
             return self._gemm_forward(cores)
         prog = self.bound.program("fwd")
@@ -371,13 +375,13 @@ class _Call:
         return grads
 
     def graphable(self) -> bool:
-        """Routes whose training step is a fixed pair of launches on caller-owned pointers."""
-        return bool(self.bound.ladder)
+        """Routes whose forward / training step is a fixed set of launches on caller-owned pointers."""
+        return bool(self.bound.ladder) or bool(self.bound.chain_rank)
 
     def train(self, cores, log_scale: float, private_ws: bool = False):
         """Fused forward + loss + reverse sweep.  Returns (loss, grads, values)."""
         if self.bound.chain_rank:
-            values, loss, grads = self._chain(cores, 1, log_scale=log_scale)
+            values, loss, grads = self._chain(cores, 1, log_scale=log_scale, private_ws=private_ws)
             return loss, grads, values
         if self.bound.ladder:
             values, loss, grads = self._ladder(cores, 1, log_scale=log_scale, private_ws=private_ws)
@@ -535,6 +539,11 @@ class B200Strategy(ContractionStrategy):
             return call, cores, _scale_of(bound, tnt)
 
         def compute_fn(cores_dict, circuit_states, measure_matrices, right_cores_dict=None):
+            if (graphs["enabled"] or _GRAPHS["enabled"]) and right_mode != "qctn" and not torch.is_grad_enabled():
+                hit = _forward_graph(cores_dict, circuit_states, measure_matrices)
+                if hit is not None:
+                    res, scale = hit
+                    return tnt_cls(res, scale=scale[0], log_scale=scale[1]) if scale is not None else res
             call, cores, scale = prepare(cores_dict, circuit_states, measure_matrices, right_cores_dict)
             if torch.is_grad_enabled() and any(c.requires_grad for c in cores):
                 res = _SweepFn.apply(call, *cores)
@@ -543,6 +552,42 @@ class B200Strategy(ContractionStrategy):
             if scale is not None:
                 return tnt_cls(res, scale=scale[0], log_scale=scale[1])
             return res
+
+        def _forward_graph(cores_dict, circuit_states, measure_matrices):
+            """Replay (or, for operands seen before, capture) the forward launches of this operand set.
+            Returns (values, scale) or None (not graphable / first sighting): the caller then launches
+            directly.  The returned tensor is the graph's output buffer (same contract as the training
+            step below)."""
+            key, tnts = _raw_ptrs(cores_dict, circuit_states, measure_matrices)
+            key = ("fwd",) + key
+            ent = graphs["entries"].get(key)
+            if ent is not None:
+                bound, graph, values, _call, nk = ent
+                graph.replay()
+                graphs["replays"] += 1
+                _lib_mod.add_graph_launches(nk)
+                return values, _scale_of(bound, dict(tnts))
+            if not graphs["seen"].get(key) or graphs["captures"] >= graphs["max_captures"]:
+                if len(graphs["seen"]) > 64:
+                    graphs["seen"].clear()
+                graphs["seen"][key] = True
+                return None
+            call, cores, scale = prepare(cores_dict, circuit_states, measure_matrices, None)
+            if not (call.graphable() and _captures_callers_buffers(key[1:], call, cores)):
+                return None
+            dev = cores[0].device
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib_mod.launch_count()
+            with torch.cuda.graph(graph):
+                values = call.forward(cores, private_ws=True)
+            nk = _lib_mod.launch_count() - n0
+            graphs["captures"] += 1
+            graph.replay()
+            if len(graphs["entries"]) >= graphs["max"]:
+                graphs["entries"].pop(next(iter(graphs["entries"])))
+            graphs["entries"][key] = (call.bound, graph, values, call, nk)
+            return values, scale
 
         # ---- CUDA-graph replay of the fused training step (opt-in) ---------------------------------
         # A training loop calls loss_and_grads with the SAME device buffers step after step (cores are

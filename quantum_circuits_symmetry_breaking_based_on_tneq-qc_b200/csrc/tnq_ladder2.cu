@@ -41,6 +41,8 @@ tnq_ladder2_kernel(const __grid_constant__ Args a, long long B, long long ntiles
     using G = Geo<R>;
     extern __shared__ __align__(16) float sm[];
     __shared__ long long tile_s;
+    // (Measured dead end: reversing the warp order of every second CTA on an SM, so that the uneven 4,4,3,3 split of
+    // the row blocks lands evenly on the four scheduler partitions, changed nothing: 1.438 vs 1.426 ms.)
     const int tid = threadIdx.x;
     constexpr int NSM = MODE == 0 ? G::FWD_FLOATS : G::TRAIN_FLOATS;
     for (int i = tid; i < NSM; i += NT) sm[i] = 0.f;
@@ -55,7 +57,8 @@ tnq_ladder2_kernel(const __grid_constant__ Args a, long long B, long long ntiles
     c.inv_count = inv_count;
     c.ck = MODE != 0 ? ckpt + (long long)blockIdx.x * G::ckpt_floats(a.n) : nullptr;
     __syncthreads();
-    if (MODE != 0) build_sources<R>(c, tid);
+    build_pos<R>(c, tid);
+    __syncthreads();
     TS ts;
     for (;;) {
         if (tid == 0) tile_s = atomicAdd(counter, 1);

@@ -131,7 +131,8 @@ struct Geo {
     static constexpr int T2_SZ = K3 * PO * S, U_SZ = K2 * PQ * S, T1_SZ = K2 * NU * 32, M_SZ = K2 * S;
     static constexpr int OFF_T2 = 0, OFF_U = OFF_T2 + T2_SZ, OFF_T1 = OFF_U + U_SZ, OFF_MA = OFF_T1 + T1_SZ,
                          OFF_MB = OFF_MA + M_SZ, OFF_VAL = OFF_MB + M_SZ;
-    static constexpr int VAL_SZ = K2 * S + 2 * S + 32;        // last step: partial values | value | d value; misc
+    static constexpr int VAL_SZ = K2 * S + 2 * S + 32;        // last step: partial values | loss terms | d value | table
+    static constexpr int OFF_POS = OFF_VAL + K2 * S + 2 * S;  // row block -> unit*32 + slot*S (27 ints)
     static constexpr int FWD_FLOATS = OFF_VAL + VAL_SZ;
     // training only
     static constexpr int OFF_DT2R = FWD_FLOATS;              // d T2 of the step above, [o''][f''][g] x position of p
@@ -140,14 +141,13 @@ struct Geo {
     static constexpr int OFF_DUP = OFF_DT2P + DT2P_SZ;       // per-row-block partial sums of d U
     static constexpr int OFF_P2P = OFF_DUP + T1_SZ;          // per-row-block part 2 of d Bs
     static constexpr int P2P_SZ = K * NU * 32;
-    static constexpr int OFF_FL = OFF_P2P + P2P_SZ;          // per-warp flush scratch [27][33]; later the row buffers
+    static constexpr int OFF_FL = OFF_P2P + P2P_SZ;          // per-warp flush scratch [27][33]
     static constexpr int FL_SZ = NW * K3 * 33;
     static constexpr int OFF_WS = OFF_FL + FL_SZ;            // per-warp row sums [NW][108]
-    static constexpr int WS_SZ = NW * 108;
-    static constexpr int OFF_SRC = OFF_WS + WS_SZ;           // flush-slot bookkeeping (ints)
-    static constexpr int SRC_SZ = 3 * 64 + 4 + NW * R * 2;
-    static constexpr int TRAIN_FLOATS = OFF_SRC + SRC_SZ;
-    static_assert(FL_SZ >= K4 * SP + K2 * SP, "row buffers alias the flush scratch");
+    static constexpr int WS_SZ = NW * 108 + 108;            // + quarter sums of d Bs part 2
+    static constexpr int OFF_ROWS = OFF_WS + WS_SZ;          // per-sample rows [81 + 9][SP]: right-copy d X, d As0
+    static constexpr int ROWS_SZ = (K4 + K2) * SP;
+    static constexpr int TRAIN_FLOATS = OFF_ROWS + ROWS_SZ;
     // global checkpoint of one tile: T2_q for q = 1 .. n-2, laid out like the shared copy
     TNQ_HOSTDEV static constexpr long long ckpt_floats(int n) { return (long long)(n - 2) * T2_SZ; }
 };
@@ -160,7 +160,7 @@ TNQ_HOSTDEV constexpr int grad_floats(int n) { return (n - 1) * GQ; }
 // Built so that the row blocks of one unit have o / (q',r) / r positions that are pairwise equal or fall
 // into different bank groups (tests/test_ladder2_emu.py checks this exhaustively).
 template <int R>
-TNQ_HD int rb_of(int u, int slot) {
+TNQ_HOSTDEV constexpr int rb_of(int u, int slot) {
     if (R == 1) return u;
     if (R == 2) {
         if (u < 9) return (u / 3) * 9 + slot * 3 + (u % 3);            // (o, q' = slot, r)
@@ -171,9 +171,8 @@ TNQ_HD int rb_of(int u, int slot) {
     if (R == 4) {
         if (u < 6) {
             const int o = u >> 1;
-            int qr;
-            if ((u & 1) == 0) qr = (slot >> 1) * 3 + (slot & 1);       // q' in {0,1} x r in {0,1}
-            else qr = slot == 0 ? 2 : (slot == 1 ? 5 : (slot == 2 ? 6 : 7));
+            const int qr = (u & 1) == 0 ? (slot >> 1) * 3 + (slot & 1)      // q' in {0,1} x r in {0,1}
+                                        : (slot == 0 ? 2 : (slot == 1 ? 5 : (slot == 2 ? 6 : 7)));
             return o * 9 + qr;
         }
         return slot < 3 ? slot * 9 + 8 : -1;
@@ -212,11 +211,29 @@ TNQ_HD int pos_q(int qr) {                       // position of (q',r) in the U 
 }
 // units [ustart(w), ustart(w+1)) belong to warp w
 template <int R>
-TNQ_HD int ustart(int w) {
+TNQ_HOSTDEV constexpr int ustart(int w) {
     if (R == 1) return w == 0 ? 0 : (w == 1 ? 7 : (w == 2 ? 14 : (w == 3 ? 21 : 27)));
     if (R == 2) return w == 0 ? 0 : (w == 1 ? 4 : (w == 2 ? 8 : (w == 3 ? 11 : 14)));
     if (R == 4) return w == 0 ? 0 : (w == 1 ? 2 : (w == 2 ? 4 : (w == 3 ? 6 : 7)));
     return w;
+}
+
+// which o the flush slot fs (0 / 1) of thread group g = warp*R + slot holds after phase_r (-1: unused):
+// a thread parks its running d T2 sum whenever the o of its row blocks changes (at most once, by construction)
+template <int R>
+TNQ_HOSTDEV constexpr int flush_o(int g, int fs) {
+    const int w = g / R, slot = g % R;
+    int cur = -1, n = 0;
+    for (int u = ustart<R>(w); u < ustart<R>(w + 1); ++u) {
+        const int id = rb_of<R>(u, slot);
+        if (id < 0) continue;
+        if (id / 9 != cur) {
+            if (cur >= 0) ++n;
+            cur = id / 9;
+            if (n == fs) return cur;
+        }
+    }
+    return -1;
 }
 
 // ---- context -----------------------------------------------------------------------------------------
@@ -283,32 +300,56 @@ TNQ_HD void fill_t2_first(const Ctx& c, int tid) {
     }
 }
 
-// phase B: U_q from M_q (task = (i, sample))
+// phase B: U_q from M_q (task = (i, p, sample); at most two tasks per thread).  The loads of M are split from
+// the arithmetic so that callers can put independent work between them (the loads come from global memory).
 template <int R>
-TNQ_HD void phase_u(const Ctx& c, int q, int tid) {
+struct UTask {
+    static constexpr int N = (K2 * Geo<R>::S + NT - 1) / NT;   // tasks per thread
+    float m[N][K];
+};
+template <int R>
+TNQ_HD void phase_u_load(const Ctx& c, int q, int tid, UTask<R>& ut) {
+    using G = Geo<R>;
+    TNQ_UNROLL
+    for (int k2 = 0; k2 < UTask<R>::N; ++k2) {
+        const int t = tid + k2 * NT;
+        if (t < K2 * G::S) {
+            const int i = t / G::S / 3, s = t % G::S;
+            TNQ_UNROLL
+            for (int k = 0; k < K; ++k) ut.m[k2][k] = load_m(c, q, c.b0 + s, i * K + k);
+        }
+    }
+}
+template <int R>
+TNQ_HD void phase_u_compute(const Ctx& c, int q, int tid, const UTask<R>& ut) {
     using G = Geo<R>;
     float* Us = c.sm + G::OFF_U;
     const int cq = q * C_STEP;
-    TNQ_NOUNROLL
-    for (int t = tid; t < K * G::S; t += NT) {
-        const int i = t / G::S, s = t % G::S;
-        float m[K];
-        TNQ_UNROLL
-        for (int k = 0; k < K; ++k) m[k] = load_m(c, q, c.b0 + s, i * K + k);
-        TNQ_UNROLL
-        for (int p = 0; p < K; ++p) {
+    TNQ_UNROLL
+    for (int k2 = 0; k2 < UTask<R>::N; ++k2) {
+        const int t = tid + k2 * NT;
+        if (t < K2 * G::S) {
+            const int ip = t / G::S, s = t % G::S, p = ip % 3;
             Vec<K2> u;
             u.zero();
             TNQ_UNROLL
             for (int k = 0; k < K; ++k) {
-                Vec<K2> xa;
-                cvec<K2>(c, xa, cq + C_XA + (p * 3 + k) * 10);     // X[p,q',k,r] over (q',r)
-                axpy(u, m[k], xa);
+                // X[p,q',k,r] over (q',r): row (p,k) of XA; p differs between the tasks of a warp, so the row is
+                // fetched per thread (an indexed constant load), not through the uniform datapath
+                const int row = cq + C_XA + (p * 3 + k) * 10;
+                TNQ_UNROLL
+                for (int qr = 0; qr < K2; ++qr) u.set(qr, fmaf(ut.m[k2][k], TNQ2_CST(row + qr), u.get(qr)));
             }
             TNQ_UNROLL
-            for (int qr = 0; qr < K2; ++qr) Us[((i * 3 + p) * G::PQ + pos_q<R>(qr)) * G::S + s] = u.get(qr);
+            for (int qr = 0; qr < K2; ++qr) Us[(ip * G::PQ + pos_q<R>(qr)) * G::S + s] = u.get(qr);
         }
     }
+}
+template <int R>
+TNQ_HD void phase_u(const Ctx& c, int q, int tid) {
+    UTask<R> ut;
+    phase_u_load<R>(c, q, tid, ut);
+    phase_u_compute<R>(c, q, tid, ut);
 }
 
 // copy of M_q for the tasks that share it: Ms[(row*3+col)][sample]
@@ -324,6 +365,7 @@ TNQ_HD void phase_a2(const Ctx& c, int q, int tid) {
     using G = Geo<R>;
     const float* T1s = c.sm + G::OFF_T1;
     float* T2s = c.sm + G::OFF_T2;
+    const int* pos = reinterpret_cast<const int*>(c.sm + G::OFF_POS);
     const int cq = q * C_STEP;
     TNQ_NOUNROLL
     for (int t = tid; t < K3 * G::S; t += NT) {
@@ -333,9 +375,7 @@ TNQ_HD void phase_a2(const Ctx& c, int q, int tid) {
         acc.zero();
         TNQ_UNROLL
         for (int ln = 0; ln < K2; ++ln) {
-            int u, slot;
-            uslot_of<R>(ln * 3 + p, u, slot);
-            const float v = T1s[((f * 3 + g) * G::NU + u) * 32 + slot * G::S + s];
+            const float v = T1s[(f * 3 + g) * G::NU * 32 + pos[ln * 3 + p] + s];
             Vec<K> b;
             cvec<K>(c, b, cq + C_BA + ln * 4);             // Bs[l,n,o] over o
             axpy(acc, v, b);
@@ -356,16 +396,19 @@ struct RowBlock {
     const float* t2;            // + ((p'*9 + f*3+g') * PO) * S
     const float* uu;            // + ((i'*3+p') * PQ) * S
 };
+// (an idle slot -- there is at most one unit with idle slots per step -- computes on row block 0 and drops its
+// results: no divergent control flow inside the hot loops)
 template <int R>
 TNQ_HD bool row_block(const Ctx& c, int u, int lane, RowBlock<R>& rb) {
     using G = Geo<R>;
     const int slot = lane / G::S, s = lane % G::S;
-    const int id = rb_of<R>(u, slot);
-    if (id < 0) return false;
+    int id = rb_of<R>(u, slot);
+    const bool active = id >= 0;
+    id = active ? id : 0;
     rb.o = id / 9, rb.qr = id % 9, rb.u = u;
     rb.t2 = c.sm + G::OFF_T2 + rb.o * G::S + s;
     rb.uu = c.sm + G::OFF_U + pos_q<R>(rb.qr) * G::S + s;
-    return true;
+    return active;
 }
 
 // V[i'] over (f,g') = sum_p' T2[f,o,g',p'] U[i',p',q',r]
@@ -407,7 +450,7 @@ TNQ_HD void phase_c_a1(const Ctx& c, int q, int warp, int lane) {
     TNQ_NOUNROLL
     for (int u = ustart<R>(warp); u < ustart<R>(warp + 1); ++u) {
         RowBlock<R> rb;
-        if (!row_block<R>(c, u, lane, rb)) continue;
+        const bool active = row_block<R>(c, u, lane, rb);
         float u9[K2];
         TNQ_UNROLL
         for (int x = 0; x < K2; ++x) u9[x] = rb.uu[x * G::PQ * G::S];
@@ -424,10 +467,12 @@ TNQ_HD void phase_c_a1(const Ctx& c, int q, int warp, int lane) {
             TNQ_UNROLL
             for (int j = 0; j < K; ++j) axpy(T1[j], E[fh / 3].get((fh % 3) * 3 + j), b);
         }
-        TNQ_UNROLL
-        for (int f2 = 0; f2 < K; ++f2)
+        if (active) {
             TNQ_UNROLL
-            for (int j = 0; j < K; ++j) T1s[((f2 * 3 + j) * G::NU + u) * 32 + lane] = T1[j].get(f2);
+            for (int f2 = 0; f2 < K; ++f2)
+                TNQ_UNROLL
+                for (int j = 0; j < K; ++j) T1s[((f2 * 3 + j) * G::NU + u) * 32 + lane] = T1[j].get(f2);
+        }
     }
 }
 
@@ -530,7 +575,7 @@ TNQ_HD void last_bwd(const Ctx& c, TS& ts, int tid) {
     const int n = c.a->n;
     const float* T2s = c.sm + G::OFF_T2;
     float* dT2r = c.sm + G::OFF_DT2R;
-    float* rows = c.sm + G::OFF_FL;        // XL rows [(g,f,h,i)][sample]
+    float* rows = c.sm + G::OFF_ROWS;      // XL rows [(g,f,h,i)][sample]
     const float* dval = c.sm + G::OFF_VAL + K2 * G::S + G::S;
     TNQ_UNROLL
     for (int x = 0; x < K2; ++x) ts.accX[x].zero();
@@ -596,34 +641,20 @@ TNQ_HD void flush_sum(const Ctx& c, int round, int warp, int lane) {
     using G = Geo<R>;
     if (lane >= K3) return;
     const float* buf = c.sm + G::OFF_FL + warp * (K3 * 33) + lane * 33;
-    float t = 0.f;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;         // (fixed association: deterministic)
     TNQ_UNROLL
-    for (int l = 0; l < 32; ++l) t += buf[l];
-    c.sm[G::OFF_WS + warp * 108 + round * K3 + lane] = t;
+    for (int l = 0; l < 32; l += 4) t0 += buf[l], t1 += buf[l + 1], t2 += buf[l + 2], t3 += buf[l + 3];
+    c.sm[G::OFF_WS + warp * 108 + round * K3 + lane] = (t0 + t1) + (t2 + t3);
 }
 
-// which o each (thread group, flush slot) of the d T2 partial sums holds: computed once per CTA
+// row block -> position of its lane run in the row-block-indexed buffers (unit*32 + slot*S): once per CTA
 template <int R>
-TNQ_HD void build_sources(const Ctx& c, int tid) {
+TNQ_HD void build_pos(const Ctx& c, int tid) {
     using G = Geo<R>;
-    int* src = reinterpret_cast<int*>(c.sm + G::OFF_SRC);       // [3][64] lists | [3] counts | ...
-    if (tid != 0) return;
-    int cnt[3] = {0, 0, 0};
-    for (int w = 0; w < NW; ++w)
-        for (int slot = 0; slot < R; ++slot) {
-            int cur = -1, fs = 0;
-            for (int u = ustart<R>(w); u < ustart<R>(w + 1); ++u) {
-                const int id = rb_of<R>(u, slot);
-                if (id < 0) continue;
-                const int o = id / 9;
-                if (o != cur) {
-                    if (cur >= 0) ++fs;
-                    cur = o;
-                    src[o * 64 + cnt[o]++] = fs * NT + w * 32 + slot * G::S;    // flush slot, first thread of the group
-                }
-            }
-        }
-    for (int o = 0; o < 3; ++o) src[3 * 64 + o] = cnt[o];
+    if (tid >= K3) return;
+    int u, slot;
+    uslot_of<R>(tid, u, slot);
+    reinterpret_cast<int*>(c.sm + G::OFF_POS)[tid] = u * 32 + slot * G::S;
 }
 
 // reverse of the fused phase (row block (o,q',r)): from d T1_{q+1}, d T2_{q+1}, T2_q, U_q
@@ -649,8 +680,8 @@ TNQ_HD void phase_r(const Ctx& c, TS& ts, int q, int warp, int lane) {
     TNQ_NOUNROLL
     for (int u = ustart<R>(warp); u < ustart<R>(warp + 1); ++u) {
         RowBlock<R> rb;
-        if (!row_block<R>(c, u, lane, rb)) continue;
-        if (rb.o != cur_o) {                // the running d T2 sum belongs to another o: park it
+        const bool active = row_block<R>(c, u, lane, rb);
+        if (active && rb.o != cur_o) {      // the running d T2 sum belongs to another o: park it
             if (cur_o >= 0) {
                 TNQ_UNROLL
                 for (int x = 0; x < K3; ++x) dT2p[(x * 2 + fs) * NT + tid] = dT2acc[x / 9].get(x % 9);
@@ -667,7 +698,7 @@ TNQ_HD void phase_r(const Ctx& c, TS& ts, int q, int warp, int lane) {
         TNQ_UNROLL
         for (int j = 0; j < K; ++j)
             TNQ_UNROLL
-            for (int f2 = 0; f2 < K; ++f2) d1[j].set(f2, dT1s[((f2 * 3 + j) * G::NU + u) * 32 + lane]);
+            for (int f2 = 0; f2 < K; ++f2) d1[j].set(f2, active ? dT1s[((f2 * 3 + j) * G::NU + u) * 32 + lane] : 0.f);
         Vec<K2> V[K];
         make_v<R>(rb, u9, V);
         {   // E' -> d Bs part 1, T1 (recomputed) -> d Bs part 2
@@ -688,15 +719,16 @@ TNQ_HD void phase_r(const Ctx& c, TS& ts, int q, int warp, int lane) {
                 }
             }
             const int r = rb.qr % 3;
+            Vec<K2> T1v;                   // over (f'',j): the order of the d T2 rows below
+            TNQ_UNROLL
+            for (int x = 0; x < K2; ++x) T1v.set(x, T1c[x % 3].get(x / 3));
             TNQ_UNROLL
             for (int o2 = 0; o2 < K; ++o2) {
-                float acc = 0.f;
+                Vec<K2> t;                 // d T2_{q+1}[f'',o'',g=j,p=r] over (f'',j): all loads first, then one dot product
                 TNQ_UNROLL
-                for (int f2 = 0; f2 < K; ++f2)
-                    TNQ_UNROLL
-                    for (int j = 0; j < K; ++j)
-                        acc = fmaf(T1c[j].get(f2), dT2r[((o2 * 9 + f2 * 3 + j) * G::PO + r) * G::S + s], acc);
-                p2p[(o2 * G::NU + u) * 32 + lane] = acc;
+                for (int x = 0; x < K2; ++x) t.set(x, dT2r[((o2 * 9 + x) * G::PO + r) * G::S + s]);
+                const float acc = dot(T1v, t, 0.f);
+                if (active) p2p[(o2 * G::NU + u) * 32 + lane] = acc;
             }
         }
         Vec<K2> dE[K];                     // [f] over (h,j) = sum_f'' Bs'[f,h,f''] d T1[f'',j]
@@ -738,7 +770,10 @@ TNQ_HD void phase_r(const Ctx& c, TS& ts, int q, int warp, int lane) {
             TNQ_UNROLL
             for (int fg = 0; fg < K2; ++fg) t.set(fg, rb.t2[(p * 9 + fg) * G::PO * G::S]);
             TNQ_UNROLL
-            for (int i = 0; i < K; ++i) dUp[((i * 3 + p) * G::NU + u) * 32 + lane] = dot(W[i], t, 0.f);
+            for (int i = 0; i < K; ++i) {
+                const float du = dot(W[i], t, 0.f);
+                if (active) dUp[((i * 3 + p) * G::NU + u) * 32 + lane] = du;
+            }
         }
     }
     if (cur_o >= 0) {
@@ -747,160 +782,184 @@ TNQ_HD void phase_r(const Ctx& c, TS& ts, int q, int warp, int lane) {
     }
 }
 
-// S.a: everything that only needs sums over partial results of phase_r
-//   left: true  -> rows 0..80 of the flushed accumulators are d X (left copy) in (g',i',h,j) order  (phase_r)
-//         false -> they are d X (right copy) in natural order (reverse of the last step)
+// sum of per-sample rows [nrows][SP] (starting at row0 of the row buffer) over the samples -> gradient slice
 template <int R>
-TNQ_HD void phase_sa(const Ctx& c, int q, bool after_r, int tid) {
+TNQ_HD void rows_to_grad(const Ctx& c, float* dst, int row0, int nrows, int tid) {
+    using G = Geo<R>;
+    if (tid >= nrows) return;
+    const float* rows = c.sm + G::OFF_ROWS + (row0 + tid) * G::SP;
+    float t0 = 0.f, t1 = 0.f;
+    for (int s = 0; s < G::S; s += 2) t0 += rows[s], t1 += rows[s + 1];
+    dst[tid] = t0 + t1;
+}
+
+// operands of phase_r(q): T2_q (checkpoint, or As0 (x) As0 for q = 0), U_q, and M_q in the buffer of q's parity.
+// prepare_r_issue starts the global loads (the checkpoint travels with cp.async on the device); prepare_r_finish
+// does the arithmetic and waits for the copy: callers put independent work between the two.
+template <int R>
+TNQ_HD void prepare_r_issue(const Ctx& c, int q, int tid, UTask<R>& ut) {
+    using G = Geo<R>;
+    if (q >= 1) {
+        float* T2s = c.sm + G::OFF_T2;
+        const float* ck = c.ck + (long long)(q - 1) * G::T2_SZ;
+        static_assert(G::T2_SZ % 4 == 0, "16-byte units");
+#ifdef __CUDA_ARCH__
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(T2s);
+        for (int e = tid; e < G::T2_SZ / 4; e += NT)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * e), "l"(ck + 4 * e) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+        for (int e = tid; e < G::T2_SZ; e += NT) T2s[e] = ck[e];
+#endif
+    }
+    phase_u_load<R>(c, q, tid, ut);
+}
+template <int R>
+TNQ_HD void prepare_r_finish(const Ctx& c, int q, int tid, const UTask<R>& ut) {
+    using G = Geo<R>;
+    if (q == 0) fill_t2_first<R>(c, tid);
+    phase_u_compute<R>(c, q, tid, ut);
+    load_ms<R>(c, q, c.sm + ((q & 1) ? G::OFF_MB : G::OFF_MA), tid);
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+// Phase X(q): everything between two big phases of the reverse sweep, in ONE phase:
+//   * flushed accumulators -> gradient slice (after phase_r(q): d X_q left copy and d Bs_{q+1} part 1; after the
+//     reverse of the last step: d X right copy in natural order, and the left-copy rows)
+//   * d Bs_{q+1} part 2: quarter sums (finished by finish_prev)
+//   * d T2_q = sum of the parked partial sums (already complete after the last step), stored where phase_r(q-1)
+//     reads it, and in the same task d T1_q = A2^T(d T2_q)                     (task = (p, f, g, sample))
+//   * d U_q = sum over o of the partial sums, right-copy d X_q per sample -> row buffer (finished by finish_prev)
+//   * the operands of phase_r(q-1)
+template <int R>
+TNQ_HD void phase_x(const Ctx& c, int q, bool after_r, int tid) {
     using G = Geo<R>;
     const float* ws = c.sm + G::OFF_WS;
+    const int* pos = reinterpret_cast<const int*>(c.sm + G::OFF_POS);
     float* gq = c.gpart + (long long)q * GQ;
+    UTask<R> ut;
+    if (q >= 1) prepare_r_issue<R>(c, q - 1, tid, ut);
     if (tid < 108) {
-        float t = 0.f;
-        TNQ_UNROLL
-        for (int w = 0; w < NW; ++w) t += ws[w * 108 + tid];
+        const float t = (ws[tid] + ws[108 + tid]) + (ws[216 + tid] + ws[324 + tid]);
         if (!after_r) {
             if (tid < K4) gq[K4 + tid] = t;
         } else if (tid < K4) {
-            const int gi = tid / 9, hj = tid % 9;
+            const int gi = tid / 9, hj = tid % 9;           // rows are (g',i',h,j): d X[g',h,i',j] (left copy)
             gq[(((gi / 3) * 3 + hj / 3) * 3 + gi % 3) * 3 + hj % 3] = t;
         } else {
-            gq[GQ + 162 + tid - K4] = t;                        // d Bs_{q+1} part 1, natural (c,e,f)
+            gq[GQ + 162 + tid - K4] = t;                    // d Bs_{q+1} part 1, natural (c,e,f)
         }
     }
-    if (!after_r) return;
-    // d Bs_{q+1} part 2: [(l,n)][o''] = sum over p and the samples
-    if (tid < K3) {
-        const int ln = tid / 3, o2 = tid % 3;
-        const float* p2p = c.sm + G::OFF_P2P;
+    if (!after_r) rows_to_grad<R>(c, gq, 0, K4, tid);       // left-copy rows of the last step
+    if (after_r && tid < 108) {
+        // d Bs_{q+1} part 2: [(l,n)][o''] = sum over p and the samples; here: four quarter sums per entry
+        const int row = tid >> 2, part = tid & 3, ln = row / 3, o2 = row % 3;
+        const float* p2p = c.sm + G::OFF_P2P + o2 * G::NU * 32;
         float t = 0.f;
+        TNQ_UNROLL
         for (int p = 0; p < K; ++p) {
-            int u, slot;
-            uslot_of<R>(ln * 3 + p, u, slot);
-            for (int s = 0; s < G::S; ++s) t += p2p[(o2 * G::NU + u) * 32 + slot * G::S + s];
+            const float* src = p2p + pos[ln * 3 + p];
+            for (int s = part; s < G::S; s += 4) t += src[s];
         }
-        gq[GQ + 189 + tid] = t;
+        c.sm[G::OFF_WS + NW * 108 + tid] = t;
     }
-    // d T2_q = sum of the parked partial sums, stored where the next phase_r / phase_sb read it
     {
         const float* dT2p = c.sm + G::OFF_DT2P;
         float* dT2r = c.sm + G::OFF_DT2R;
-        const int* src = reinterpret_cast<const int*>(c.sm + G::OFF_SRC);
-        TNQ_NOUNROLL
-        for (int t = tid; t < K4 * G::S; t += NT) {
-            const int s = t % G::S, e = t / G::S;              // e = x*3 + o, x = p'*9 + f*3 + g'
-            const int o = e % 3, x = e / 3, p = x / 9, fg = x % 9;
-            const int cnt = src[3 * 64 + o];
-            float v = 0.f;
-            for (int k = 0; k < cnt; ++k) {
-                const int w = src[o * 64 + k];
-                v += dT2p[(x * 2 + w / NT) * NT + (w % NT) + s];
-            }
-            dT2r[((o * 9 + fg) * G::PO + p) * G::S + s] = v;
-        }
-    }
-    // d U_q = sum over o of the partial sums; right-copy d X_q[p',q',k,r] = sum_i' M_q[i',k] d U[i',p',q',r], per sample
-    {
-        const float* dUp = c.sm + G::OFF_DUP;
-        const float* MA = c.sm + G::OFF_MA;
-        float* rows = c.sm + G::OFF_FL;
+        float* dT1s = c.sm + G::OFF_T1;
+        const int cq = q * C_STEP;
         TNQ_NOUNROLL
         for (int t = tid; t < K3 * G::S; t += NT) {
-            const int s = t % G::S, e = t / G::S;              // e = p'*9 + qr
-            const int p = e / 9, qr = e % 9;
+            const int s = t % G::S, x = t / G::S, p = x / 9, fg = x % 9;    // x = p*9 + f*3 + g
+            float d[K] = {0.f, 0.f, 0.f};
+            if (after_r) {
+                TNQ_UNROLL
+                for (int g = 0; g < NW * R; ++g)
+                    TNQ_UNROLL
+                    for (int fs = 0; fs < 2; ++fs) {
+                        const int o = flush_o<R>(g, fs);    // (compile time after unrolling)
+                        if (o >= 0) d[o] += dT2p[(x * 2 + fs) * NT + (g / R) * 32 + (g % R) * G::S + s];
+                    }
+                TNQ_UNROLL
+                for (int o = 0; o < K; ++o) dT2r[((o * 9 + fg) * G::PO + p) * G::S + s] = d[o];
+            } else {
+                TNQ_UNROLL
+                for (int o = 0; o < K; ++o) d[o] = dT2r[((o * 9 + fg) * G::PO + p) * G::S + s];
+            }
+            if (q >= 1) {
+                Vec<K2> out;               // d T1_q[f,(l,n),p,g] over (l,n) = sum_o Bs_q[l,n,o] d T2_q[f,o,g,p]
+                out.zero();
+                TNQ_UNROLL
+                for (int o = 0; o < K; ++o) {
+                    Vec<K2> bb;
+                    cvec<K2>(c, bb, cq + C_BB + o * 10);
+                    axpy(out, d[o], bb);
+                }
+                float* dst = dT1s + fg * G::NU * 32 + s;
+                TNQ_UNROLL
+                for (int ln = 0; ln < K2; ++ln) dst[pos[ln * 3 + p]] = out.get(ln);
+            }
+        }
+    }
+    if (after_r) {
+        const float* dUp = c.sm + G::OFF_DUP;
+        const float* Mq = c.sm + ((q & 1) ? G::OFF_MB : G::OFF_MA);
+        float* rows = c.sm + G::OFF_ROWS;
+        TNQ_NOUNROLL
+        for (int t = tid; t < K3 * G::S; t += NT) {
+            const int s = t % G::S, e = t / G::S, p = e / 9, qr = e % 9;    // e = p'*9 + qr
+            const int a0 = pos[qr] + s, a1 = pos[9 + qr] + s, a2 = pos[18 + qr] + s;
             float du[K];
             TNQ_UNROLL
             for (int i = 0; i < K; ++i) {
-                float v = 0.f;
-                TNQ_UNROLL
-                for (int o = 0; o < K; ++o) {
-                    int u, slot;
-                    uslot_of<R>(o * 9 + qr, u, slot);
-                    v += dUp[((i * 3 + p) * G::NU + u) * 32 + slot * G::S + s];
-                }
-                du[i] = v;
+                const float* dd = dUp + (i * 3 + p) * G::NU * 32;
+                du[i] = (dd[a0] + dd[a1]) + dd[a2];
             }
             TNQ_UNROLL
             for (int k = 0; k < K; ++k) {
                 float v = 0.f;
                 TNQ_UNROLL
-                for (int i = 0; i < K; ++i) v = fmaf(MA[(i * 3 + k) * G::S + s], du[i], v);
+                for (int i = 0; i < K; ++i) v = fmaf(Mq[(i * 3 + k) * G::S + s], du[i], v);
                 rows[(((p * 3 + qr / 3) * 3 + k) * 3 + qr % 3) * G::SP + s] = v;
             }
         }
     }
+    if (q >= 1) prepare_r_finish<R>(c, q - 1, tid, ut);
 }
 
-// sum of the per-sample rows [81][SP] over the samples -> gradient slice
+// what phase X(q) left unfinished (run one barrier later): right-copy d X_q rows and d Bs_{q+1} part 2 -> gradient slice
 template <int R>
-TNQ_HD void rows_to_grad(const Ctx& c, float* dst, int row0, int nrows, int tid) {
+TNQ_HD void finish_prev(const Ctx& c, int q, int tid) {
     using G = Geo<R>;
-    if (tid >= nrows) return;
-    const float* rows = c.sm + G::OFF_FL + (row0 + tid) * G::SP;
-    float t = 0.f;
-    for (int s = 0; s < G::S; ++s) t += rows[s];
-    dst[tid] = t;
+    // (given to the LAST warps: they own one row block less in the phase_r that follows)
+    rows_to_grad<R>(c, c.gpart + (long long)q * GQ + K4, 0, K4, NT - 1 - tid);
+    if (tid < K3) {
+        const float* qs = c.sm + G::OFF_WS + NW * 108 + tid * 4;
+        c.gpart[(long long)(q + 1) * GQ + 189 + tid] = (qs[0] + qs[1]) + (qs[2] + qs[3]);
+    }
 }
 
-// S.b: d T1_q = A2^T (d T2_q)  (task = (f,p,g,sample)); q = 0: d As0 per sample instead
+// first step: d As0[e][f'] = sum_{p,o} d T2_0[f',o,e,p] As0[p][o] + sum_{g,f} d T2_0[f,f',g,e] As0[g][f], per sample
 template <int R>
-TNQ_HD void phase_sb(const Ctx& c, int q, int tid) {
+TNQ_HD void das0_rows(const Ctx& c, int tid) {
     using G = Geo<R>;
     const float* dT2r = c.sm + G::OFF_DT2R;
-    if (q == 0) {
-        // d As0[e][f'] = sum_{p,o} d T2[f',o,e,p] As0[p][o] + sum_{g,f} d T2[f,f',g,e] As0[g][f]
-        float* rows = c.sm + G::OFF_FL + K4 * G::SP;
-        const int base = (c.a->n - 1) * C_STEP + T_AS0;
-        TNQ_NOUNROLL
-        for (int t = tid; t < K2 * G::S; t += NT) {
-            const int s = t % G::S, ef = t / G::S, e = ef / 3, f1 = ef % 3;
-            float v = 0.f;
-            for (int a1 = 0; a1 < K; ++a1)
-                for (int b1 = 0; b1 < K; ++b1) {
-                    // first term: (p,o) = (a1,b1);  second term: (g,f) = (a1,b1)
-                    v = fmaf(dT2r[((b1 * 9 + f1 * 3 + e) * G::PO + a1) * G::S + s], TNQ2_CST(base + a1 * 3 + b1), v);
-                    v = fmaf(dT2r[((f1 * 9 + b1 * 3 + a1) * G::PO + e) * G::S + s], TNQ2_CST(base + a1 * 3 + b1), v);
-                }
-            rows[ef * G::SP + s] = v;
-        }
-        return;
-    }
-    float* dT1s = c.sm + G::OFF_T1;
-    const int cq = q * C_STEP;
+    float* rows = c.sm + G::OFF_ROWS + K4 * G::SP;
+    const int base = (c.a->n - 1) * C_STEP + T_AS0;
     TNQ_NOUNROLL
-    for (int t = tid; t < K3 * G::S; t += NT) {
-        const int s = t % G::S, x = t / G::S;
-        const int g = x % 3, p = (x / 3) % 3, f = x / 9;
-        Vec<K2> out;                       // over (l,n)
-        out.zero();
-        TNQ_UNROLL
-        for (int o = 0; o < K; ++o) {
-            Vec<K2> bb;
-            cvec<K2>(c, bb, cq + C_BB + o * 10);
-            axpy(out, dT2r[((o * 9 + f * 3 + g) * G::PO + p) * G::S + s], bb);
-        }
-        TNQ_UNROLL
-        for (int ln = 0; ln < K2; ++ln) {
-            int u, slot;
-            uslot_of<R>(ln * 3 + p, u, slot);
-            dT1s[((f * 3 + g) * G::NU + u) * 32 + slot * G::S + s] = out.get(ln);
-        }
+    for (int t = tid; t < K2 * G::S; t += NT) {
+        const int s = t % G::S, ef = t / G::S, e = ef / 3, f1 = ef % 3;
+        float v = 0.f;
+        for (int a1 = 0; a1 < K; ++a1)
+            for (int b1 = 0; b1 < K; ++b1) {
+                // first term: (p,o) = (a1,b1);  second term: (g,f) = (a1,b1)
+                v = fmaf(dT2r[((b1 * 9 + f1 * 3 + e) * G::PO + a1) * G::S + s], TNQ2_CST(base + a1 * 3 + b1), v);
+                v = fmaf(dT2r[((f1 * 9 + b1 * 3 + a1) * G::PO + e) * G::S + s], TNQ2_CST(base + a1 * 3 + b1), v);
+            }
+        rows[ef * G::SP + s] = v;
     }
-}
-
-// S.c: operands of phase_r(q): T2_q (checkpoint, or As0 (x) As0 for q = 0), U_q, M_q
-template <int R>
-TNQ_HD void phase_sc(const Ctx& c, int q, int tid) {
-    using G = Geo<R>;
-    if (q == 0) {
-        fill_t2_first<R>(c, tid);
-    } else {
-        float* T2s = c.sm + G::OFF_T2;
-        const float* ck = c.ck + (long long)(q - 1) * G::T2_SZ;
-        for (int e = tid; e < G::T2_SZ; e += NT) T2s[e] = ck[e];
-    }
-    phase_u<R>(c, q, tid);
-    load_ms<R>(c, q, c.sm + G::OFF_MA, tid);
 }
 
 }  // namespace tnq_l2
@@ -956,34 +1015,36 @@ TNQ_HD void tile_sweep(const Ctx& c, TNQ2_THREAD_PARAM) {
     TNQ2_PH(last_value<R, MODE>(c, tid);)
     if (MODE == 0) return;
     // ------------------------------- reverse sweep -------------------------------
-    TNQ2_PH(
+    TNQ2_PHW(
         if (MODE == 1 && tid == 0) {
             float t = 0.f;
             for (int s = 0; s < G::S; ++s) t += c.sm[G::OFF_VAL + K2 * G::S + s];
             *c.lpart = t;
         }
         last_bwd<R>(c, ts, tid);)
-    TNQ2_PH(rows_to_grad<R>(c, c.gpart + (long long)(n - 2) * GQ, 0, K4, tid);)
 #define TNQ2_FLUSH(ROUND)                                                  \
     TNQ2_PHW(flush_put<R, ROUND>(c, ts, TNQ2_WARP, TNQ2_LANE);)             \
     TNQ2_PHW(flush_sum<R>(c, ROUND, TNQ2_WARP, TNQ2_LANE);)
+#define TNQ2_FLUSH_LAST(ROUND)                                             \
+    TNQ2_PHW(flush_put<R, ROUND>(c, ts, TNQ2_WARP, TNQ2_LANE);)             \
+    TNQ2_PH(flush_sum<R>(c, ROUND, TNQ2_WARP, TNQ2_LANE);)
     TNQ2_FLUSH(0)
     TNQ2_FLUSH(1)
-    TNQ2_FLUSH(2)
-    TNQ2_PH()
-    TNQ2_PH(phase_sa<R>(c, n - 2, false, tid); phase_sb<R>(c, n - 2, tid);)
+    TNQ2_FLUSH_LAST(2)
+    TNQ2_PH(phase_x<R>(c, n - 2, false, tid);)
     for (int q = n - 3; q >= 0; --q) {
-        TNQ2_PH(phase_sc<R>(c, q, tid);)
-        TNQ2_PH(phase_r<R>(c, ts, q, TNQ2_WARP, TNQ2_LANE);)
+        TNQ2_PHW(
+            if (q < n - 3) finish_prev<R>(c, q + 1, tid);
+            phase_r<R>(c, ts, q, TNQ2_WARP, TNQ2_LANE);)
         TNQ2_FLUSH(0)
         TNQ2_FLUSH(1)
         TNQ2_FLUSH(2)
-        TNQ2_FLUSH(3)
-        TNQ2_PH()
-        TNQ2_PH(phase_sa<R>(c, q, true, tid);)
-        TNQ2_PH(rows_to_grad<R>(c, c.gpart + (long long)q * GQ + K4, 0, K4, tid); phase_sb<R>(c, q, tid);)
+        TNQ2_FLUSH_LAST(3)
+        TNQ2_PH(phase_x<R>(c, q, true, tid);)
     }
+    TNQ2_PH(finish_prev<R>(c, 0, tid); das0_rows<R>(c, tid);)
     TNQ2_PH(rows_to_grad<R>(c, c.gpart + 162, K4, K2, tid);)
+#undef TNQ2_FLUSH_LAST
 #undef TNQ2_FLUSH
 #undef TNQ2_WARP
 #undef TNQ2_LANE

@@ -33,8 +33,7 @@ static void run(const Args& a, long long B, const float* seed, float* values, fl
     c.inv_count = 1.0f / (float)B;
     c.ck = ck.data();
     std::vector<TS> tss(NT);
-    if (MODE != 0)
-        for (int tid = 0; tid < NT; ++tid) build_sources<R>(c, tid);
+    for (int tid = 0; tid < NT; ++tid) build_pos<R>(c, tid);
     for (long long tile = 0; tile < ntiles; ++tile) {
         c.b0 = tile * G::S;
         c.gpart = gparts.data() + (size_t)tile * ng;
