@@ -47,12 +47,17 @@ WORKLOADS = {
                      name="24-qubit 2-layer merged MPS QCTN, K=3, forward only, batch 16384"),
     "cfg4": dict(kind="mps", n=16, K=64, batch=256, mode="train", dtype="complex64", weak=True, near_identity=True,
                  name="cfg4: 16-qubit MPS QCTN, bond 64, complex64, fwd+loss+bwd, batch 256 per GPU (tcgen05 GEMM path)"),
+    "cfg4-128": dict(kind="mps", n=16, K=128, batch=8, mode="train", dtype="complex64", weak=True, near_identity=True,
+                     name="cfg4: 16-qubit MPS QCTN, bond 128, complex64, fwd+loss+bwd, batch 8 per GPU (tcgen05 GEMM path; 32 per GPU does not fit 180 GB with the cores' 64 GB)"),
     "cfg4-32": dict(kind="mps", n=16, K=32, batch=256, mode="train", dtype="complex64", weak=True, near_identity=True,
                     name="16-qubit MPS QCTN, bond 32, complex64, fwd+loss+bwd, batch 256 per GPU (tcgen05 GEMM path)"),
     "cfg2": dict(kind="mps", n=16, K=3, batch=4096, mode="fwd", dtype="float32",
                  name="cfg2: 16-qubit MPS QCTN, K=3, forward probabilities, batch 4096"),
     "cfg2-large": dict(kind="mps", n=16, K=3, batch=1 << 20, mode="fwd", dtype="float32",
                        name="cfg2-large: 16-qubit MPS QCTN, K=3, forward probabilities, batch 2^20"),
+    "cfg2-large-x": dict(kind="mps", n=16, K=3, batch=1 << 20, mode="fwdx", dtype="float32",
+                         name="cfg2-large with generate_data fused into the sweep (EngineSiamese.contract_from_x): "
+                              "16-qubit MPS QCTN, K=3, forward probabilities from x, batch 2^20"),
     "cfg2-train": dict(kind="mps", n=16, K=3, batch=1 << 18, mode="train", dtype="float32",
                        name="16-qubit MPS QCTN, K=3, fwd+loss+bwd, batch 2^18"),
 }
@@ -170,8 +175,10 @@ def time_reference(args, wl):
     def run_once(xb):
         if ref_eng is not None:
             with rh.quiet():
+                t0 = time.perf_counter()                 # (fwdx: generating the matrices is part of the step)
                 mx, _ = ref_eng.generate_data(xb, K=wl["K"], ret_type="TNTensor")
-                t0 = time.perf_counter()
+                if wl["mode"] != "fwdx":
+                    t0 = time.perf_counter()
                 if wl["mode"] == "train":
                     ref_eng.contract_with_compiled_strategy_for_gradient(ref_q, states, mx)
                 else:
@@ -324,6 +331,8 @@ def main():
     mx_host = [m.tensor.cpu().pin_memory() for m in mx_dev]
     mx_scales = [(m.scale, m.log_scale) for m in mx_dev]
     h2d_bytes = sum(m.numel() * m.element_size() for m in mx_host)
+    if wl["mode"] == "fwdx":
+        h2d_bytes = x_local.numel() * 4
 
     fn = engine._compiled(qctn, states, mx_dev, True, "symmetric")
     cores_dict = {c: qctn.cores_weights[c] for c in names}
@@ -364,15 +373,22 @@ def main():
         flat /= world
         return flat
 
+    if dist is not None and train and oneshot is not None and not args.no_graphs:
+        # the exchange is recorded into the training step's CUDA graph: a step is one graph launch
+        fn.set_graph_epilogue(lambda loss0, grads: average(loss0, grads))
+
     def step_device():
         if train:
             loss, grads, _vals, _sc = fn.loss_and_grads(cores_dict, states, mx_dev)
-            if dist is not None:
+            if dist is not None and fn.graph_stats["last_extra"] is None:
                 average(loss, grads)
             return loss
         with torch.no_grad():
+            if wl["mode"] == "fwdx":
+                return engine.contract_from_x(qctn, states, x_dev, K=K)
             return fn(cores_dict, states, mx_dev).tensor
 
+    x_dev = x_local.to(dev).contiguous()
     use_graphs = train and not args.no_graphs
     # e2e input pipeline: two sets of STATIC device buffers (the CUDA-graph contract of
     # EngineSiamese.enable_cuda_graphs) filled from pinned host memory on a copy stream; the copy of
@@ -394,7 +410,21 @@ def main():
             ev.record(copy_stream)
         return ev
 
+    x_host = x_local.contiguous().pin_memory()
+    x_static = [torch.empty_like(x_host, device=dev) for _ in range(2)]
+
+    def step_e2e_x():
+        """fwdx: the step's input is x itself (B x n floats from pinned host memory)."""
+        cur = pipe["i"] % 2
+        x_static[cur].copy_(x_host, non_blocking=True)
+        with torch.no_grad():
+            out = engine.contract_from_x(qctn, states, x_static[cur], K=K)
+        pipe["i"] += 1
+        return float(out.sum().item())
+
     def step_e2e():
+        if wl["mode"] == "fwdx":
+            return step_e2e_x()
         cur = pipe["i"] % 2
         if pipe["ready"] is None:
             pipe["ready"] = issue_copy(cur)
@@ -404,7 +434,10 @@ def main():
         if train:
             loss, grads = engine.contract_with_compiled_strategy_for_gradient(qctn, states, mxs)
             if dist is not None:
-                val = float(average(loss, grads)[-1].item())
+                avg = fn.graph_stats["last_extra"]          # the exchange ran inside the step's graph ...
+                if avg is None:
+                    avg = average(loss, grads)              # ... or the step was launched directly
+                val = float(avg[-1].item())
             else:
                 val = float(loss.item())
         else:
@@ -479,7 +512,7 @@ def main():
         prog = bound.program("train" if train else "fwd")
         info = prog.info(B * bound.plan.nb)
         flops_launch = prog.prog.flops_per_sample * B * bound.plan.nb
-    mx_bytes = B * nq * K * K * esz
+    mx_bytes = B * nq * (1 if wl["mode"] == "fwdx" else K * K) * esz
     core_bytes = sum(v.numel() * esz for v in cores_cpu.values())
     alg_bytes = mx_bytes + B * 4 + core_bytes * (2 if train else 1)
     peaks = {}
@@ -553,7 +586,7 @@ def main():
             "dtype": "f32" if esz == 4 else "c64 (real fp32 arithmetic: 3xTF32 on tcgen05)", "data": "synthetic",
             "config": {"workload": wl["name"], "global_batch": B_global, "per_gpu_batch": B, "qubits": nq, "K": K,
                        "cores": len(names), "l2": "flushed between timed steps (256 MiB write)",
-                       "cuda_graphs": bool(train and not args.no_graphs),
+                       "cuda_graphs": bool(not args.no_graphs and (bound.ladder or bound.chain_rank) and wl["mode"] != "fwdx"),
                        "parallelism": f"batch sharded over {world} GPU(s); cores replicated; "
                                       + (("one one-shot NVLink all-reduce (tnq_allreduce_oneshot, symmetric memory) of grads+loss per step"
                                           if oneshot is not None else "one packed NCCL all-reduce of grads+loss per step")

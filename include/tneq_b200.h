@@ -97,6 +97,18 @@ int tnq_mps_chain(int K, int n, const float* const* cores, const float* const* s
                   float* const* grads, double log_scale, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * The same sweep (forward values) with the measurement matrices generated IN REGISTERS from x: opt-in fusion of
+ * EngineSiamese.generate_data (tneq_qc/core/engine_siamese.py:59-111 weights and Hermite recurrence, :133-254)
+ * into the contraction.  phi_k(x) = w_k sqrt(exp(-x^2/2)) He_k(x), Mx = phi phi^T / scale[q] with
+ * scale[q] = max over the batch of |phi phi^T| (TNTensor.auto_scale, tn_tensor.py:72-85) computed by a first
+ * kernel.  The sweep reads n floats per sample instead of n K^2.
+ *   x: sample b, qubit q at x[b * xs_b + q * xs_q];  weights[K] (host);  scale[n] (device, out)
+ *   values[B]: contraction of the scaled matrices; the true value is values * prod_q scale[q].
+ */
+int tnq_mps_chain_x(int K, int n, const float* const* cores, const float* const* states, const float* x, int64_t xs_b,
+                    int64_t xs_q, const float* weights, int64_t B, float* scale, float* values, void* stream);
+
+/*
  * Warp-level sweep for TWO-LAYER merged MPS networks (QCTN.merge(mps_n, mps_n), reference
  * tneq_qc/core/qctn.py:1296-1506; BASELINE cfg3), float32, edge rank K in {2,3}, n >= 3: the greedy
  * sweep greedy_strategy.py:461-598 with its rank-6 environment kept in shared memory by the warp that

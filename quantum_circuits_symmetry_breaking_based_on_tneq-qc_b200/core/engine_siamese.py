@@ -22,6 +22,7 @@ import math
 from typing import Any, List, Optional, Tuple, Union
 
 import numpy as np
+import torch
 
 from ..backends.backend_factory import BackendFactory
 from ..backends.backend_interface import ComputeBackend
@@ -140,7 +141,7 @@ class EngineSiamese:
         """Per-sample value <s|U^dag (x_q M_q) U|s>; complex dtypes return the squared
         modulus of that (the reference's convention)."""
         fn = self._compiled(qctn, circuit_states_list, measure_input_list, measure_is_matrix, right_qctn)
-        cores = {name: qctn.cores_weights[name] for name in qctn.cores}
+        cores = qctn.cores_weights      # (the network's own dict: compute functions recognise repeated operands by identity)
         rcores = None
         if isinstance(right_qctn, QCTN) or hasattr(right_qctn, "cores_weights"):
             rcores = {name: right_qctn.cores_weights[name] for name in right_qctn.cores}
@@ -154,6 +155,76 @@ class EngineSiamese:
             res.scale_to(1.0)
             return be.abs_square(res.tensor)
         return be.abs_square(res)
+
+    # ---- cores only (einsum_strategy.py:137-194, engine.py:228-252, qctn.py:986-991) -------------
+    @staticmethod
+    def build_core_only_expression(qctn):
+        """(einsum equation, core shapes) for contracting the cores with nothing attached: the symbol
+        bookkeeping of EinsumStrategy.build_core_only_expression (one symbol per open circuit edge, in
+        order of appearance -- these form the output --, one per core-to-core bond)."""
+        from .qctn import symbol_of
+        sid = 0
+        left, right, bond = [], "", {}
+        for info in qctn.adjacency_table:
+            idx, eq = info["core_idx"], ""
+            for lst in (info["in_edge_list"], info["out_edge_list"]):
+                for e in lst:
+                    if e["neighbor_idx"] == -1:
+                        sym = symbol_of(sid)
+                        sid += 1
+                        right += sym
+                    else:
+                        key = tuple(sorted([e["neighbor_idx"], idx])) + (e["qubit_idx"],)
+                        if key not in bond:
+                            bond[key] = symbol_of(sid)
+                            sid += 1
+                        sym = bond[key]
+                    eq += sym
+            left.append(eq)
+        shapes = [tuple((w.tensor if isinstance(w, TNTensor) else w).shape) for w in (qctn.cores_weights[c] for c in qctn.cores)]
+        return ",".join(left) + "->" + right, shapes
+
+    def contract_core_only(self, qctn):
+        """The dense operator of the network (open circuit inputs and outputs kept, no batch, no measurement):
+        what the reference's pruning experiment (symmetry_breaking_quantum.py) contracts.  Small networks only
+        (the result has prod(open edge ranks) elements).  Cores are contracted pairwise on the device in the
+        order the equation lists them; TNTensor cores enter with their scale."""
+        eq, _ = self.build_core_only_expression(qctn)
+        tensors = []
+        for c in qctn.cores:
+            w = qctn.cores_weights[c]
+            tensors.append(w.tensor * w.scale if isinstance(w, TNTensor) else w)
+        return self.backend.einsum(eq, *tensors)
+
+    def contract_from_x(self, qctn, circuit_states_list, x, K: int = None, ret_type="tensor"):
+        """Opt-in (no reference counterpart as an API): the values that
+        `contract_with_compiled_strategy(qctn, states, generate_data(x, K, ret_type='TNTensor')[0])` returns, with
+        generate_data (engine_siamese.py:133-254) fused into the sweep where the network allows it -- single-layer
+        MPS, float32: the measurement matrices are generated in registers and the kernel reads n floats per sample
+        instead of n K^2 (csrc/tnq_chain.cu: tnq_mps_chain_x).  Other networks materialise the matrices on the
+        device and take the usual route."""
+        if K is None:
+            K = self.mx_K
+        be = self.backend
+        x = be.convert_to_tensor(x)
+        if K > self.mx_K or K > self.mx_weights.shape[0]:
+            self.mx_weights = self._init_mx_weights(K)
+            self.mx_K = K
+        fused = None
+        if x.dtype == torch.float32 and x.is_cuda and x.dim() == 2:
+            probe = [torch.empty((x.shape[0], K, K), dtype=x.dtype, device="meta")] * x.shape[1]
+            fn = self._compiled(qctn, circuit_states_list, probe, True, "symmetric")
+            if hasattr(fn, "forward_from_x"):
+                cores = {name: qctn.cores_weights[name] for name in qctn.cores}
+                fused = fn.forward_from_x(cores, circuit_states_list, x, [float(w) for w in self._mx_weights_np[:K].astype(np.float32)])
+        if fused is None:
+            mats, _ = self.generate_data(x, K=K, ret_type="TNTensor")
+            return self.contract_with_compiled_strategy(qctn, circuit_states_list, mats, ret_type=ret_type)
+        values, scale = fused
+        if ret_type == "TNTensor":
+            sc = scale.double().cpu()
+            return TNTensor(values, float(sc.prod()), float(sc.log().sum()))
+        return values * scale.double().prod().to(values.dtype)
 
     def contract_with_compiled_strategy_for_gradient(self, qctn, circuit_states_list, measure_input_list,
                                                      measure_is_matrix=True, right_qctn="symmetric",
@@ -170,7 +241,7 @@ class EngineSiamese:
 
         trainable = [(o, n) for o, n in owners if raw_of(o.cores_weights[n]).requires_grad]
         if fused and hasattr(fn, "loss_and_grads"):
-            cores = {n: qctn.cores_weights[n] for n in qctn.cores}
+            cores = qctn.cores_weights
             rcores = {n: right_qctn.cores_weights[n] for n in right_qctn.cores} if has_right else None
             loss, grads, _values, _scale = fn.loss_and_grads(cores, circuit_states_list, measure_input_list,
                                                              right_cores_dict=rcores)

@@ -460,6 +460,101 @@ tnq_chain_fwd2_kernel(const __grid_constant__ ChainArgs a, long long B, float* _
     }
 }
 
+// ---- opt-in: measurement matrices generated in registers from x (EngineSiamese.generate_data fused into the sweep) ----
+// Reference: tneq_qc/core/engine_siamese.py:59-111 (weights, Hermite recurrence) and :133-254 (generate_data):
+//   phi_k(x) = w_k * sqrt(exp(-x^2 / 2)) * He_k(x),  He_0 = 1, He_1 = x, He_i = x He_{i-1} - (i-1) He_{i-2},
+//   Mx = phi phi^T, wrapped as TNTensor: divided by its global abs-max over the batch (tn_tensor.py:72-85).
+// The chain kernel then reads n floats per sample instead of n K^2: the HBM roofline of the sweep itself moves.
+struct HermiteW {
+    float w[4];
+};
+template <int K>
+__device__ __forceinline__ void hermite_phi(float x, const HermiteW& hw, float (&phi)[K]) {
+    const float g = sqrtf(expf(-(x * x) / 2.0f));
+    float hm2 = 1.0f, hm1 = x;
+    phi[0] = hw.w[0] * g;                         // (w * g) * H, as the reference associates it
+    if (K > 1) phi[1] = hw.w[1] * g * x;
+#pragma unroll
+    for (int i = 2; i < K; ++i) {
+        const float h = x * hm1 - (float)(i - 1) * hm2;
+        phi[i] = hw.w[i] * g * h;
+        hm2 = hm1, hm1 = h;
+    }
+}
+
+// scale[q] = max over the batch of max_{i,j} |phi_i phi_j| = max_b (max_i |phi_i|)^2  (positive floats order like ints)
+template <int K>
+__global__ void tnq_hermite_scale_kernel(const float* __restrict__ x, long long xs_b, long long xs_q, long long B, int n,
+                                         HermiteW hw, float* __restrict__ scale) {
+    const int q = blockIdx.y;
+    float best = 0.f;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        float phi[K];
+        hermite_phi<K>(__ldg(x + b * xs_b + q * xs_q), hw, phi);
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < K; ++i) a = fmaxf(a, fabsf(phi[i]));
+        best = fmaxf(best, a * a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(scale) + q, __float_as_int(best));
+}
+
+template <int K>
+__global__ void __launch_bounds__(CHAIN_THREADS, K <= 3 ? 4 : 1)
+tnq_chain_fwd2x_kernel(const __grid_constant__ ChainArgs a, long long B, const float* __restrict__ x, long long xs_b,
+                       long long xs_q, HermiteW hw, const float* __restrict__ scale, float* __restrict__ values) {
+    constexpr int K3 = K * K * K;
+    extern __shared__ float sm[];
+    const int n = a.n;
+    float* Ls = sm;                                   // [n-1][K3]
+    float* inv_s = sm + (n - 1) * K3;                 // [n]
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (n - 1) * K3; i += blockDim.x) {
+        const int q = i / K3, r = i % K3, c = r / (K * K), e = (r / K) % K, f = r % K;
+        float s = 0.f;
+        for (int d = 0; d < K; ++d) s = fmaf(__ldg(a.core[q] + ((c * K + d) * K + e) * K + f), __ldg(a.state[q + 1] + d), s);
+        Ls[i] = s;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) inv_s[i] = 1.0f / __ldg(scale + i);
+    __syncthreads();
+    float s0[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) s0[i] = __ldg(a.state[0] + i);
+    const long long ntiles = (B + 63) / 64;
+    for (long long wi = (long long)blockIdx.x * warps + warp; wi < ntiles; wi += (long long)gridDim.x * warps) {
+        const long long b0 = wi * 64, ba = b0 + lane, bb = b0 + 32 + lane;
+        const float* xa = x + (ba < B ? ba : B - 1) * xs_b;
+        const float* xb = x + (bb < B ? bb : B - 1) * xs_b;
+        F2 env[K][K], M[K][K];
+#pragma unroll
+        for (int h = 0; h < K; ++h)
+#pragma unroll
+            for (int c = 0; c < K; ++c) env[h][c] = F2{s0[h] * s0[c], s0[h] * s0[c]};
+        float xna = __ldg(xa), xnb = __ldg(xb);
+        for (int q = 0; q < n; ++q) {
+            float pa[K], pb[K];
+            hermite_phi<K>(xna, hw, pa);
+            hermite_phi<K>(xnb, hw, pb);
+            if (q + 1 < n) xna = __ldg(xa + (q + 1) * xs_q), xnb = __ldg(xb + (q + 1) * xs_q);   // next qubit's x in flight
+            const float is = inv_s[q];
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+#pragma unroll
+                for (int j = 0; j < K; ++j) M[i][j] = F2{pa[i] * pa[j] * is, pb[i] * pb[j] * is};
+            if (q < n - 1) chain_step2<K>(env, Ls + q * K3, M);
+        }
+        F2 val{0.f, 0.f};                              // "acd,adc->a"
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int d = 0; d < K; ++d) val = fma2(env[c][d], M[d][c], val);
+        if (ba < B) values[ba] = val.lo;
+        if (bb < B) values[bb] = val.hi;
+    }
+}
+
 // Training / seeded reverse sweep with TWO samples per thread (MODE 1 / 2, batch-contiguous
 // measurements, K <= 3): the same packed arithmetic as tnq_chain_fwd2_kernel for the forward sweep
 // (left environments taped in local memory) and for the reverse sweep, whose per-h slices keep the
@@ -777,6 +872,57 @@ int tnq_mps_chain(int K, int n, const float* const* cores, const float* const* s
         case 3: return launch_chain<3>(a, B, mode, seed, values, loss, (float)log_scale, workspace, workspace_bytes, st);
         default: return launch_chain<4>(a, B, mode, seed, values, loss, (float)log_scale, workspace, workspace_bytes, st);
     }
+}
+
+/* Forward values with the measurement matrices generated in registers from x (opt-in, no reference counterpart
+ * as an API: it computes what contract(generate_data(x, ret_type='TNTensor')) computes, engine_siamese.py:133-254).
+ *   x: sample b, qubit q at x[b * xs_b + q * xs_q];  weights[K]: the Hermite normalisation weights (:59-80)
+ *   scale[n] (device, out): per-qubit TNTensor scale = global abs-max of phi phi^T over the batch
+ *   values[B] (out): the contraction of the SCALED matrices; the true value is values * prod_q scale[q]. */
+int tnq_mps_chain_x(int K, int n, const float* const* cores, const float* const* states, const float* x, int64_t xs_b,
+                    int64_t xs_q, const float* weights, int64_t B, float* scale, float* values, void* stream) {
+    if (n < 2 || n > MAXQ) return tnq_internal_fail("tnq_mps_chain_x: between 2 and " + std::to_string(MAXQ) + " qubits");
+    if (K < 2 || K > 4) return tnq_internal_fail("tnq_mps_chain_x: edge rank must be 2, 3 or 4");
+    if (!cores || !states || !x || !weights || !scale || !values || B <= 0) return tnq_internal_fail("tnq_mps_chain_x: bad arguments");
+    ChainArgs a;
+    a.n = n;
+    for (int q = 0; q < n; ++q) {
+        a.state[q] = states[q];
+        a.mx[q] = nullptr;
+        a.mx_stride[q] = 0;
+        a.core[q] = q < n - 1 ? cores[q] : nullptr;
+        a.grad[q] = nullptr;
+        if (!states[q] || (q < n - 1 && !cores[q])) return tnq_internal_fail("tnq_mps_chain_x: null pointer at qubit " + std::to_string(q));
+    }
+    HermiteW hw;
+    for (int i = 0; i < 4; ++i) hw.w[i] = i < K ? weights[i] : 0.f;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaMemsetAsync(scale, 0, sizeof(float) * n, st);
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaMemsetAsync(scale)");
+    long long wantb = (B + 255) / 256;
+    dim3 gs((unsigned)(wantb < 1 ? 1 : (wantb > 4 * sms ? 4 * sms : wantb)), (unsigned)n);
+    const int K3 = K * K * K;
+    const size_t smem2 = sizeof(float) * ((size_t)(n - 1) * K3 + (size_t)n);
+    long long want2 = (B + 2 * CHAIN_THREADS - 1) / (2 * CHAIN_THREADS);
+    const long long cap2 = (long long)sms * 4;
+    const int grid2 = (int)(want2 < 1 ? 1 : (want2 > cap2 ? cap2 : want2));
+#define TNQ_CHAIN_X(KK)                                                                                              \
+    tnq_hermite_scale_kernel<KK><<<gs, 256, 0, st>>>(x, xs_b, xs_q, B, n, hw, scale);                                \
+    tnq_internal_count_launch();                                                                                     \
+    tnq_chain_fwd2x_kernel<KK><<<grid2, CHAIN_THREADS, smem2, st>>>(a, B, x, xs_b, xs_q, hw, scale, values);         \
+    tnq_internal_count_launch();
+    switch (K) {
+        case 2: TNQ_CHAIN_X(2) break;
+        case 3: TNQ_CHAIN_X(3) break;
+        default: TNQ_CHAIN_X(4) break;
+    }
+#undef TNQ_CHAIN_X
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_mps_chain_x launch");
+    return 0;
 }
 
 }  // extern "C"

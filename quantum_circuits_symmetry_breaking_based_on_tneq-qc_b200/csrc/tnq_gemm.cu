@@ -270,15 +270,15 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
             const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
             const long long k0 = (long long)kb * BK;
             if (SMALLK) {
-                if (kb >= NSTAGE) {
+                float4 v[4];                  // A then B: half the registers in flight
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = load_unit<ALIGNED>(A + k0, lda, M - m0, K - k0, warp * 4 + i, lane);
+                if (kb >= NSTAGE) {           // the drain of the previous k-block while the loads of A are in flight
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     drain_add(tlane + (uint32_t)(s * BN), sum, !have);
                     have = true;
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 }
-                float4 v[4];                  // A then B: half the registers in flight
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = load_unit<ALIGNED>(A + k0, lda, M - m0, K - k0, warp * 4 + i, lane);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) store_unit(v[i], warp * 4 + i, lane, st, st + TILE_BYTES);
 #pragma unroll

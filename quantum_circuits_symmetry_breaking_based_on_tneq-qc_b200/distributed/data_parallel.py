@@ -77,6 +77,7 @@ class DataParallelTrainer:
         self.accumulated_grads: Optional[List[torch.Tensor]] = None
         self.accumulation_count = 0
         self._oneshot, self._oneshot_tried = None, False
+        self._graphs, self._epi_fn, self._ls_dev = False, None, None
         # lock-step QR retractions on every rank: a private stream, not the process-global one
         self.optimizer.opt_state["rng"] = random.Random(self.config.seed)
 
@@ -153,6 +154,40 @@ class DataParallelTrainer:
         out = self.comm.allreduce_list(list(grads) + [loss_t], op=ReduceOp.AVG)
         return out[:-1], out[-1][0]
 
+    def enable_cuda_graphs(self, flag: bool = True):
+        """One CUDA-graph launch per training step (no reference counterpart): the fused contraction kernels
+        AND the one-shot NVLink exchange of gradients + loss are captured together (the engine's graph replay,
+        EngineSiamese.enable_cuda_graphs, with the exchange as its epilogue).  Same contract as the engine's
+        replay: cores updated in place (the 'sgdg' flat step does that), batches copied into static buffers."""
+        self._graphs = bool(flag)
+        self.engine.enable_cuda_graphs(flag)
+        self.optimizer.opt_state["pingpong"] = bool(flag)     # optim/steps.py: cores alternate between two buffers
+        if not flag and self._epi_fn is not None:
+            self._epi_fn.set_graph_epilogue(None)
+            self._epi_fn = None
+
+    def _graph_epilogue_for(self, fn, grads_like_numel: int, device):
+        """Register the exchange as the epilogue of fn's training graph (once per compiled function)."""
+        if fn is self._epi_fn:
+            return
+        if self._epi_fn is not None:
+            self._epi_fn.set_graph_epilogue(None)
+        self._epi_fn = None
+        red = self._oneshot_for(grads_like_numel, device)
+        if red is None or not hasattr(fn, "set_graph_epilogue"):
+            return
+        self._ls_dev = torch.zeros(1, dtype=torch.float32, device=device)
+
+        def epilogue(loss0, grads):
+            base = getattr(grads[0], "_base", None)
+            if base is None or base.dtype != torch.float32 or base.numel() != grads_like_numel:
+                return None
+            # the captured kernel computes the loss with log_scale = 0; the step's log_scale arrives in _ls_dev
+            return red.mean(base, loss0.reshape(1) - self._ls_dev)
+
+        fn.set_graph_epilogue(epilogue)
+        self._epi_fn = fn
+
     def accumulate_gradients(self, grads: List[torch.Tensor]):
         if self.accumulated_grads is None:
             self.accumulated_grads = [g.clone() for g in grads]
@@ -169,8 +204,31 @@ class DataParallelTrainer:
         return avg
 
     def train_step(self, data: Dict, circuit_states_list: List) -> float:
-        loss, grads = self.compute_local_gradients(data, circuit_states_list)
         k = self.config.gradient_accumulation_steps
+        fn = None
+        if self._graphs and k == 1 and self.world_size > 1 and "measure_input_list" in data:
+            mi = data["measure_input_list"]
+            fn = self.engine._compiled(self.qctn, circuit_states_list, mi, data.get("measure_is_matrix", True), "symmetric")
+            n_grad = sum((w.tensor if hasattr(w, "scale") else w).numel() for w in self.qctn.cores_weights.values())
+            self._graph_epilogue_for(fn, n_grad, self.comm.device)
+            if self._epi_fn is fn:
+                ls = sum(float(getattr(m, "log_scale", 0.0) or 0.0) for m in (mi.values() if isinstance(mi, dict) else mi)
+                         if m is not None)
+                ls += sum(float(w.log_scale) for w in self.qctn.cores_weights.values() if hasattr(w, "log_scale"))
+                self._ls_dev.fill_(ls)
+        loss, grads = self.compute_local_gradients(data, circuit_states_list)
+        if fn is not None and self._epi_fn is fn and fn.graph_stats["last_extra"] is not None:
+            out = fn.graph_stats["last_extra"]             # exchange done inside the step's graph
+            pieces, at = [], 0
+            for g in grads:
+                pieces.append(out[at:at + g.numel()].reshape(g.shape))
+                at += g.numel()
+            self.optimizer.step(self.qctn, pieces)
+            loss_avg = float(out[-1])
+            if loss_avg != loss_avg and self._oneshot is not None:
+                self._oneshot.check()
+            self.optimizer.iter += 1
+            return loss_avg
         if k > 1:
             self.accumulate_gradients(grads)
             if (self.global_step + 1) % k == 0:

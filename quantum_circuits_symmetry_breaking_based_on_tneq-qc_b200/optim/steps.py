@@ -159,7 +159,16 @@ def _sgdg_flat_step(params, grads, state, lr, mom, out):
                 state["momentum_buffer"][i] = vflat[off: off + n].view(c, r)
             state["_flat_v"] = vflat
             state["_flat_poff"] = [int(x) for x in p_off]
-        flat = torch.cat([p.reshape(-1) for p in params])
+        if state.get("pingpong"):
+            # two persistent parameter buffers used alternately: the cores of step i+2 live where those of step i
+            # lived, so a training loop presents only two sets of addresses (CUDA-graph replay, DataParallelTrainer.
+            # enable_cuda_graphs); the tensors returned two steps ago are overwritten
+            bufs = state.setdefault("_flat_p", [torch.empty(int(sum(sizes)), dtype=torch.float32, device=dev) for _ in range(2)])
+            flat = bufs[state.get("_flat_turn", 0) & 1]
+            state["_flat_turn"] = state.get("_flat_turn", 0) + 1
+            torch.cat([p.reshape(-1) for p in params], out=flat)
+        else:
+            flat = torch.cat([p.reshape(-1) for p in params])
         p_off = state["_flat_poff"]
         rng = state.get("rng", random)
         for n in range(len(params)):

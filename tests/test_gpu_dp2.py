@@ -88,6 +88,20 @@ assert err < 2e-5, f"data-parallel cores differ from the single-process schedule
 for a, b in zip(losses, ref_losses):
     assert abs(a - b) <= 1e-5 * abs(b), (a, b)
 assert losses[-1] < losses[0]
+
+# the same schedule with ONE CUDA-graph launch per step (contraction + exchange captured together, cores
+# ping-ponging between two buffers): same numbers, and the graph really replays
+eng3, q3, st3, data3 = fresh(dev)
+tr3 = DataParallelTrainer(eng3, q3, cfg, comm=comm)
+tr3.enable_cuda_graphs(True)
+mine3 = tr3.partition_data(data3)
+tr3.sync_model_weights()
+losses3 = [tr3.train_step(mine3[0], st3) for _ in range(STEPS + 6)]
+fn3 = eng3._compiled(q3, st3, mine3[0]["measure_input_list"], True, "symmetric")
+assert fn3.graph_stats["replays"] >= 2, fn3.graph_stats
+for a, b in zip(losses3, losses):
+    assert abs(a - b) <= 2e-5 * abs(b), (a, b)
+tr3.enable_cuda_graphs(False)
 comm.barrier()
 comm.destroy()
 print("DP2-OK", rank, err)

@@ -43,8 +43,21 @@ def _bound(eng, q, st, mx):
     return next(iter(eng._compiled(q, st, mx, True, "symmetric").plans.values()))
 
 
-@pytest.mark.parametrize("n,K,B", [(3, 3, 4), (5, 3, 100), (24, 3, 50), (9, 2, 333), (24, 2, 64)])
-def test_ladder_vs_oracle(n, K, B, built_lib):
+@pytest.fixture(params=["warp-level", "second-generation"])
+def generation(request):
+    """Edge rank 3 has two implementations of the sweep: csrc/tnq_ladder.cu (default) and, with
+    TNQ_LADDER_V2=1, csrc/tnq_ladder2.cu (lanes = samples, constant-memory operands, recomputed
+    environment).  Both are held to the same parity bar."""
+    if request.param == "second-generation":
+        os.environ["TNQ_LADDER_V2"] = "1"
+    yield request.param
+    os.environ.pop("TNQ_LADDER_V2", None)
+
+
+@pytest.mark.parametrize("n,K,B", [(3, 3, 4), (5, 3, 100), (24, 3, 50), (9, 2, 333), (24, 2, 64), (7, 3, 150)])
+def test_ladder_vs_oracle(n, K, B, built_lib, generation):
+    if generation == "second-generation" and K != 3:
+        pytest.skip("the second-generation kernel covers edge rank 3")
     graph = merged_graph(n, K)
     names, table, nq, cores, states, mxs = well_conditioned_case(graph, K, B, "float32", seed=n + K)
     want = oc.forward(graph, cores, states, clone_mx(mxs))
@@ -95,7 +108,7 @@ def test_ladder_vs_vm_route(built_lib):
     assert abs(la - lb) < 1e-4 * abs(lb)
 
 
-def test_long_chain(built_lib):
+def test_long_chain(built_lib, generation):
     """Long chains.  Random-data values underflow float32 at these lengths, so the checks are the
     normalisation known answer (orthogonal cores + identity measurements => 1), agreement of the two
     CUDA routes at 40 qubits (the VM's operand table ends at 192 inputs), and at 64 qubits -- where
@@ -135,7 +148,7 @@ def test_long_chain(built_lib):
                 assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-7
 
 
-def test_cfg3_full_size_properties(built_lib):
+def test_cfg3_full_size_properties(built_lib, generation):
     """cfg3 size (24 qubits, batch 16384): normalisation known answer, ragged batches, and the
     loss / gradient of a batch equal to the sample-weighted mean over its two halves."""
     n, K, B = 24, 3, 16384

@@ -186,3 +186,54 @@ def test_large_batch_and_ragged_tail(built_lib):
         got = eng.contract_with_compiled_strategy(q, [s.cuda() for s in states],
                                                   [_to_dev(m, torch.device("cuda:0")) for m in clone_mx(mxs)])
         assert rel_err(got, want) < 2e-5
+
+
+@pytest.mark.parametrize("n,K,B", [(16, 3, 1000), (6, 2, 130), (5, 4, 77), (2, 3, 9)])
+def test_contract_from_x_fused_generate_data(n, K, B, built_lib):
+    """EngineSiamese.contract_from_x (generate_data fused into the chain kernel, tnq_mps_chain_x)
+    against the oracle's generate_data (engine_siamese.py:133-254) + forward, and against this package's own
+    unfused route; the per-qubit TNTensor scales (tn_tensor.py:72-85) are reproduced too."""
+    graph = _graph("mps", n, K)
+    torch.manual_seed(n * 7 + K)
+    names, table, nq = oc.parse_graph(graph)
+    cores = oc.random_cores(table)
+    states = oc.unit_states(nq, K)
+    x = torch.randn(B, nq)
+    mx, _ = oc.generate_data(x, K, torch.float32, "TNTensor")
+    want = oc.forward(graph, cores, states, clone_mx(mx))
+    truth = oc.forward(graph, {k: v.double() for k, v in cores.items()}, [s.double() for s in states],
+                       [upcast(m, torch.float64) for m in clone_mx(mx)])
+    be, eng = _engine("float32", K, built_lib)
+    q = tneq_b200.QCTN(graph, backend=be)
+    for k, v in cores.items():
+        q.cores_weights[k] = v.cuda()
+    st = [s.cuda() for s in states]
+    launches0 = tneq_b200._lib.launch_count()
+    got = eng.contract_from_x(q, st, x.cuda(), K=K)
+    assert tneq_b200._lib.launch_count() == launches0 + 2, "scale kernel + fused chain kernel"
+    assert got.shape == want.shape
+    assert rel_err(got, want) < 1e-5
+    assert elem_rel_err(got.double(), truth) < max(1e-5, NOISE_FACTOR * elem_rel_err(want.double(), truth))
+    res = eng.contract_from_x(q, st, x.cuda(), K=K, ret_type="TNTensor")
+    ref_scale = 1.0
+    for m in mx:
+        ref_scale *= m.scale
+    assert abs(res.scale - ref_scale) <= 1e-5 * ref_scale
+    unfused = eng.contract_with_compiled_strategy(q, st, eng.generate_data(x.cuda(), K=K, ret_type="TNTensor")[0])
+    assert rel_err(got, unfused) < 1e-5
+
+
+def test_contract_from_x_other_networks_take_the_usual_route(built_lib):
+    K, n, B = 3, 5, 40
+    graph = _graph("merged", n, K)
+    names, table, nq, cores, states, mxs = make_case(graph, K, B, "float32")
+    be, eng = _engine("float32", K, built_lib)
+    q = tneq_b200.QCTN(graph, backend=be)
+    for k, v in cores.items():
+        q.cores_weights[k] = v.cuda()
+    st = [s.cuda() for s in states]
+    torch.manual_seed(3)
+    x = torch.randn(B, nq).cuda()
+    a = eng.contract_from_x(q, st, x, K=K)
+    b = eng.contract_with_compiled_strategy(q, st, eng.generate_data(x, K=K, ret_type="TNTensor")[0])
+    assert torch.equal(a, b)

@@ -184,3 +184,41 @@ def test_right_qctn_given_as_second_network(ref):
     assert len(gg) == len(wg) == 2 * len(names)
     for g, w in zip(gg, wg):
         assert rel_err(g, w) < 5e-5
+
+
+def test_checkpoint_interchange_and_core_only_contraction(ref, tmp_path):
+    """the safetensors checkpoint layout (qctn.py:902-964) written by the reference loads here and
+    vice versa, and the cores-only contraction (einsum_strategy.py:137-194 + engine.py:228-252) of the loaded
+    network equals a float64 einsum of the same equation on the CPU."""
+    rh, ns = ref
+    import tneq_b200
+    K, n = 2, 5
+    graph = tneq_b200.QCTNHelper.generate_example_graph(n=n, graph_type="tree", dim_char=str(K))
+    names, table, nq = oc.parse_graph(graph)
+    torch.manual_seed(8)
+    cores = oc.random_cores(table)
+    be_cpu, eng_cpu, be_gpu, eng_gpu = _engines(ns, K)
+    with contextlib.redirect_stdout(io.StringIO()):
+        qref = ns.QCTN(graph, backend=be_cpu)
+    for k, v in cores.items():
+        qref.cores_weights[k] = v.clone()
+    f1, f2 = str(tmp_path / "ref.safetensors"), str(tmp_path / "ours.safetensors")
+    qref.save_cores(f1, metadata={"note": "written by the reference"})
+    ours_be = tneq_b200.BackendFactory.create_backend("b200", device=DEV, dtype="float32")
+    qo = tneq_b200.QCTN.from_pretrained(graph, f1, backend=ours_be)
+    assert qo._loaded_metadata.get("note") == "written by the reference"
+    for k, v in cores.items():
+        w = qo.cores_weights[k]
+        assert rel_err((w.tensor * w.scale).cpu(), v) < 1e-6
+    qo.save_cores(f2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        qback = ns.QCTN.from_pretrained(graph, f2, backend=be_cpu)
+    for k, v in cores.items():
+        w = qback.cores_weights[k]
+        assert rel_err(w.tensor * w.scale, v) < 1e-6
+    eng = tneq_b200.EngineSiamese(backend=ours_be, strategy_mode="balanced", mx_K=K)
+    eq, shapes = eng.build_core_only_expression(qo)
+    dense = eng.contract_core_only(qo)
+    want = torch.einsum(eq, *[cores[k].double() for k in names])
+    assert dense.device.type == "cuda" and tuple(dense.shape) == tuple(want.shape)
+    assert rel_err(dense.double().cpu(), want) < 1e-5

@@ -198,3 +198,27 @@ def test_reference_plugin_registration():
     # leave the reference's registry as we found it for the other tests
     ns.StrategyCompiler.MODES["balanced"].remove("b200")
     ns.StrategyCompiler.MODES["full"].remove("b200")
+
+
+def test_core_only_expression_matches_reference():
+    """EngineSiamese.build_core_only_expression reproduces the reference's einsum bookkeeping for the cores-only
+    contraction (einsum_strategy.py:137-194) on MPS, tree, wall and merged graphs (reference checkout needed)."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference tree not present on this machine")
+    ns = rh.load()
+    import importlib
+    es = importlib.import_module("tneq_qc.contractor.einsum_strategy")
+    builder = next(getattr(es, n) for n in dir(es) if hasattr(getattr(es, n), "build_core_only_expression"))
+    be, _ = rh.make_engine()
+    for kind, n, K in [("mps", 5, 2), ("tree", 6, 2), ("wall", 4, 2), ("mps", 4, 3)]:
+        graph = tneq_b200.QCTNHelper.generate_example_graph(n=n, graph_type=kind, dim_char=str(K))
+        with rh.quiet():
+            qr = ns.QCTN(graph, backend=be)
+        want_eq, want_shapes = builder.build_core_only_expression(qr)
+        q = tneq_b200.QCTN(graph)
+        for c in q.cores:
+            q.cores_weights[c] = torch.zeros(q.core_shape(c))
+        got_eq, got_shapes = tneq_b200.EngineSiamese.build_core_only_expression(q)
+        assert got_eq == want_eq, (kind, got_eq, want_eq)
+        assert [tuple(s_) for s_ in got_shapes] == [tuple(s_) for s_ in want_shapes]
