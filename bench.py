@@ -544,7 +544,7 @@ def main():
     try:
         table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         ent = table.get(f"{args.workload}:{B}")
-        if ent and world == 1 and ent.get("csrc_sha256") == ge.csrc_digest():
+        if ent and world == 1 and ent.get("csrc_sha256") == ge.csrc_digest(ent.get("files")):
             traffic = ent["dram_bytes_per_launch"]
     except Exception:
         traffic = None
@@ -593,6 +593,14 @@ def main():
                                          if world > 1 else "no collective"),
                        "oneshot_vs_nccl_rel_err": checked.get("err_vs_nccl")},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
+    if wl["mode"] == "fwdx":
+        # the same job without the fusion: x -> generate_data (torch, device) -> contraction, timed the same way
+        def step_unfused():
+            with torch.no_grad():
+                mats, _ = engine.generate_data(x_dev, K=K, ret_type="TNTensor")
+                return engine.contract_with_compiled_strategy(qctn, states, mats)
+        ms_unf, _, _ = timed(step_unfused, max(3, args.steps // 4), 3)
+        line["config"]["unfused_from_x_ms_per_step"] = ms_unf / max(3, args.steps // 4)
     if e2e is not None:
         line["e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

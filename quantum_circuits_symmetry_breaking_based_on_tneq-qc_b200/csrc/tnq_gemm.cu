@@ -214,12 +214,31 @@ __device__ __forceinline__ void store_tile(const float (&sum)[64], float* xpose,
     }
 }
 
+// the 12 MMAs of one k-block (issued by one thread), then the commits that release the stage / signal completion
+__device__ __forceinline__ void issue_kblock(uint32_t st, uint32_t tmem_h, uint32_t tmem_corr, int kb, bool last,
+                                             uint32_t empty_bar, uint32_t accum_bar) {
+#pragma unroll
+    for (int j = 0; j < BK / 8; ++j) {
+        const uint32_t ko = (uint32_t)j * 2u * 128u;     // two 16-byte chunks per K=8 step
+        const uint64_t a_hi = umma_desc(st + ko), a_lo = umma_desc(st + TILE_BYTES + ko);
+        const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES + ko), b_lo = umma_desc(st + 3 * TILE_BYTES + ko);
+        // correction terms: one accumulator for the whole k-loop (Ootomo & Yokota's split accumulators);
+        // hi*hi: a fresh accumulator per k-block, drained and summed round-to-nearest on the CUDA cores
+        umma_tf32(tmem_corr, a_lo, b_hi, (kb | j) != 0);
+        umma_tf32(tmem_corr, a_hi, b_lo, 1u);
+        umma_tf32(tmem_h, a_hi, b_hi, j != 0);
+    }
+    umma_commit(empty_bar);                              // frees the stage (and its accumulator) when the MMAs retire
+    if (last) umma_commit(accum_bar);                    // everything complete
+}
+
 // SMALLK (K <= 256: a handful of k-blocks, the regime of the bond-64 sweep where K = 2 x bond):
-// one pipeline stage, one hi*hi + one correction accumulator = 256 TMEM columns and <= 112
-// registers, so that TWO CTAs share an SM and one tile's epilogue overlaps the other tile's loads
-// and MMAs.
+// one pipeline stage, one hi*hi + one correction accumulator = 256 TMEM columns, <= 112 registers and EIGHT
+// warps (lane 0 of warp 0 issues the MMAs after its own loads; with one stage the producers wait for the MMAs
+// anyway), so that TWO CTAs share an SM -- the register file is partitioned per scheduler: 2 x 8 warps x 112
+// registers fit, 2 x 9 do not -- and one tile's epilogue overlaps the other tile's loads and MMAs.
 template <bool ALIGNED, bool SMALLK>
-__global__ void __maxnreg__(SMALLK ? 112 : 168)
+__global__ void __maxnreg__(SMALLK ? 128 : 168)
 tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, long long M,
                        long long N, long long K, long long lda, long long ldb, long long ldc, long long strideA,
                        long long strideB, long long strideC, int accumulate) {
@@ -243,7 +262,8 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == PRODUCERS / 32) {
+    constexpr int ALLOC_WARP = SMALLK ? 0 : PRODUCERS / 32;
+    if (warp == ALLOC_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
                      "r"(NCOLS)
                      : "memory");
@@ -306,6 +326,13 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
             mbar_arrive(full0 + 8 * s);          // (also: this stage's accumulator has been read)
+            if (SMALLK && warp == 0) {           // no separate issuer warp in this variant
+                mbar_wait(full0 + 8 * s, phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0)
+                    issue_kblock(st, tmem_base + (uint32_t)(s * BN), tmem_corr, kb, kb == nkb - 1, empty0 + 8 * s, accum_bar);
+                __syncwarp();
+            }
         }
         // ---------------- epilogue ----------------
         mbar_wait(accum_bar, 0);
@@ -320,36 +347,21 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
         float* xpose = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // pipeline smem is idle now
         store_tile(sum, xpose, lane, C, ldc, m0 + quad * 32, n0 + chalf * 64, M, N, accumulate);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    } else {
+    } else if (!SMALLK) {
         // ---------------- MMA issuer ----------------
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % NSTAGE;
             const uint32_t phase = (uint32_t)(kb / NSTAGE) & 1u;
             mbar_wait(full0 + 8 * s, phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
-                const uint32_t tmem_h = tmem_base + (uint32_t)(s * BN);
-#pragma unroll
-                for (int j = 0; j < BK / 8; ++j) {
-                    const uint32_t ko = (uint32_t)j * 2u * 128u;     // two 16-byte chunks per K=8 step
-                    const uint64_t a_hi = umma_desc(st + ko), a_lo = umma_desc(st + TILE_BYTES + ko);
-                    const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES + ko), b_lo = umma_desc(st + 3 * TILE_BYTES + ko);
-                    // correction terms: one accumulator for the whole k-loop (Ootomo & Yokota's split
-                    // accumulators); hi*hi: a fresh accumulator per k-block, drained and summed round-to-
-                    // nearest on the CUDA cores (header comment)
-                    umma_tf32(tmem_corr, a_lo, b_hi, (kb | j) != 0);
-                    umma_tf32(tmem_corr, a_hi, b_lo, 1u);
-                    umma_tf32(tmem_h, a_hi, b_hi, j != 0);
-                }
-                umma_commit(empty0 + 8 * s);                          // frees the stage (and its accumulator) when the MMAs retire
-                if (kb == nkb - 1) umma_commit(accum_bar);            // everything complete
-            }
+            if (lane == 0)
+                issue_kblock(smem_base + (uint32_t)s * STAGE_BYTES, tmem_base + (uint32_t)(s * BN), tmem_corr, kb, kb == nkb - 1,
+                             empty0 + 8 * s, accum_bar);
             __syncwarp();
         }
     }
     __syncthreads();
-    if (warp == PRODUCERS / 32) {
+    if (warp == ALLOC_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NCOLS) : "memory");
     }
 }
@@ -365,7 +377,7 @@ extern "C" int tnq_gemm_kernel_attrs(int aligned, int smallk, int* out) {
     const cudaError_t e = cudaFuncGetAttributes(&at, kern);
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncGetAttributes(gemm)");
     out[0] = at.numRegs, out[1] = at.maxThreadsPerBlock, out[2] = (int)at.sharedSizeBytes;
-    out[3] = GEMM_THREADS;
+    out[3] = smallk ? PRODUCERS : GEMM_THREADS;
     return 0;
 }
 
@@ -383,7 +395,7 @@ extern "C" int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(gemm)");
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
-    kern<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC,
+    kern<<<grid, smallk ? PRODUCERS : GEMM_THREADS, smem, (cudaStream_t)stream>>>(A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC,
                                                              accumulate);
     tnq_internal_count_launch();
     e = cudaGetLastError();

@@ -172,6 +172,30 @@ def test_sampling_shape_and_bounds(built_lib):
     assert (samples >= -5).all() and (samples <= 5).all()
 
 
+def test_sampling_linear_method_equals_grid_method(built_lib):
+    """sample(method='linear') -- K^2 contractions per sample and qubit instead of grid_size, using the
+    exact linearity of the value in one qubit's measurement matrix -- draws the same samples as the reference's
+    grid procedure (method='grid') from the same random numbers, on a chain, a two-layer and a tree network; and
+    it launches far fewer contractions' worth of samples."""
+    for kind, n, K in (("mps", 6, 3), ("merged", 4, 3), ("tree", 6, 2)):
+        graph = _graph(kind, n, K)
+        be, eng = _engine("float32", K, built_lib)
+        torch.manual_seed(5)
+        names, table, nq = oc.parse_graph(graph)
+        cores = oc.random_cores(table)
+        q = tneq_b200.QCTN(graph, backend=be)
+        for k, v in cores.items():
+            q.cores_weights[k] = v.cuda()
+        st = [s.cuda() for s in oc.unit_states(nq, K)]
+        out = {}
+        for method in ("grid", "linear"):
+            torch.manual_seed(77)
+            torch.cuda.manual_seed(77)
+            out[method] = eng.sample(q, st, num_samples=64, K=K, bounds=[-5, 5], grid_size=60, method=method)
+        assert tuple(out["linear"].shape) == (64, nq)
+        assert (out["linear"] - out["grid"]).abs().max().item() < 2e-3, kind
+
+
 def test_large_batch_and_ragged_tail(built_lib):
     """Batch sizes that are not a multiple of the tile, and one bigger than a wave."""
     K, n = 3, 8
