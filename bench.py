@@ -233,6 +233,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="do not replay the training step from a CUDA graph")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after the warm-up, run ONE step between cudaProfilerStart/Stop and exit (ncu --profile-from-start off: "
+                         "the launch list of exactly one steady-state step)")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="average gradients with NCCL instead of the one-shot NVLink kernel (tnq_allreduce_oneshot)")
     args = ap.parse_args()
@@ -476,6 +479,16 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), launches, cs.summary()
 
+    if args.profile_step:
+        for _ in range(args.warmup):
+            step_device()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        step_device()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled": "one step", "workload": wl["name"]}), flush=True)
+        return
     ms_total, launches, clocks = timed(step_device, args.steps, args.warmup)
     ms_step = ms_total / args.steps
     value = B_global / (ms_step * 1e-3)

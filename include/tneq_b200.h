@@ -129,7 +129,7 @@ int64_t tnq_mps_ladder_workspace_bytes(int K, int n, int64_t B, int mode);
  * a step fused with phase A of the next), T2 the only per-sample state checkpointed to HBM, the environment
  * re-derived in the reverse sweep.  Same arguments and modes as tnq_mps_ladder.  The constant pool is one
  * per device: launches must be stream-ordered with each other (one stream, or events between streams).
- *   tnq_mps_ladder2_geometry: out[5] = {R, samples per tile, tiles, CTAs, dynamic shared bytes} for (n, B, mode).
+ *   tnq_mps_ladder2_geometry: out[6] = {R, samples per tile, tiles, CTAs, dynamic shared bytes, warps per CTA} for (n, B, mode).
  */
 int64_t tnq_mps_ladder2_workspace_bytes(int n, int64_t B, int mode);
 int tnq_mps_ladder2_geometry(int n, int64_t B, int mode, int64_t* out);

@@ -605,50 +605,38 @@ class B200Strategy(ContractionStrategy):
 
         def _raw_ptrs(cores_dict, circuit_states, measure_matrices):
             """Identity of the operand buffers: address, dtype, shape and strides of every operand
-            (a graph bakes all of them in).  Fast path: a training / serving loop passes the SAME container
-            and tensor objects step after step; if every operand `is` the object seen last time with this
-            container triple, its key is reused (47 identity checks instead of 47 data_ptr() calls -- the
-            difference between 27 and ~12 us per call at BASELINE cfg2's batch of 4096).  Contract (as for graph
-            replay in general): tensors are updated in place, not re-pointed with `.data =` / `set_()`."""
+            (a graph bakes all of them in).  A training / serving loop presents the SAME tensor objects step
+            after step (possibly inside fresh containers and fresh TNTensor wrappers): the raw tensors are
+            collected (one pass), looked up by their object ids, and if every one `is` the tensor seen last time
+            the stored key is reused -- ~100 identity checks instead of ~100 data_ptr() / stride() calls.
+            Contract (as for graph replay in general): tensors are updated in place, not re-pointed with
+            `.data =` / `set_()`."""
             T = torch.Tensor
-            fast_key = (id(cores_dict), id(circuit_states), id(measure_matrices))
-            memo = graphs["memo"].get(fast_key)
-            if memo is not None:
-                objs, key, tnts = memo
-                cur = [cores_dict[k] for k in core_names]
-                cur += list(_items(circuit_states, nq).values())
-                cur += list(_items(measure_matrices, nq).values())
-                if len(cur) == len(objs) and all(a is b and (isinstance(a, T) or a is None or a.tensor is t)
-                                                 for a, (b, t) in zip(cur, objs)):
-                    return key, tnts
-            ptrs, tnts = [], []
+            raws, tnts = [], []
             for k in core_names:
                 v = cores_dict[k]
                 if not isinstance(v, T):
                     tnts.append((("core", k), v))
                     v = v.tensor
-                ptrs.append((v.data_ptr(), v.dtype, v.shape, v.stride()))
+                raws.append(v)
             for q, v in _items(circuit_states, nq).items():
                 if not isinstance(v, T):
                     tnts.append((("state", q), v))
                     v = v.tensor
-                ptrs.append((v.data_ptr(), v.dtype, v.shape, v.stride()))
+                raws.append(v)
             for q, v in _items(measure_matrices, nq).items():
-                if v is None:
-                    ptrs.append(0)
-                    continue
-                if not isinstance(v, T):
+                if v is not None and not isinstance(v, T):
                     tnts.append((("mx", q), v))
                     v = v.tensor
-                ptrs.append((v.data_ptr(), v.dtype, v.shape, v.stride()))
-            key = tuple(ptrs)
-            objs = []
-            for v in [cores_dict[k] for k in core_names] + list(_items(circuit_states, nq).values()) + \
-                    list(_items(measure_matrices, nq).values()):
-                objs.append((v, None if (v is None or isinstance(v, T)) else v.tensor))
+                raws.append(v)
+            ids = tuple(map(id, raws))
+            memo = graphs["memo"].get(ids)
+            if memo is not None and all(a is b for a, b in zip(raws, memo[0])):
+                return memo[1], tnts
+            key = tuple(0 if v is None else (v.data_ptr(), v.dtype, v.shape, v.stride()) for v in raws)
             if len(graphs["memo"]) > 16:
                 graphs["memo"].clear()
-            graphs["memo"][fast_key] = (objs, key, tnts)
+            graphs["memo"][ids] = (raws, key)
             return key, tnts
 
         def _captures_callers_buffers(key, call, cores):

@@ -33,12 +33,13 @@ __global__ void tnq_l2_prep_kernel(const __grid_constant__ Args a, float* __rest
     if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
 }
 
-template <int R, int MODE>
+template <int R, int NW, int MODE>
 __global__ void __maxnreg__(MODE == 0 ? 128 : 255)
 tnq_ladder2_kernel(const __grid_constant__ Args a, long long B, long long ntiles, const float* __restrict__ seed,
                    float* __restrict__ values, float* __restrict__ gparts, float* __restrict__ lparts,
                    float* __restrict__ ckpt, int* __restrict__ counter, float log_scale, float inv_count) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
+    constexpr int NT = NW * 32;
     extern __shared__ __align__(16) float sm[];
     __shared__ long long tile_s;
     // (Measured dead end: reversing the warp order of every second CTA on an SM, so that the uneven 4,4,3,3 split of
@@ -57,7 +58,7 @@ tnq_ladder2_kernel(const __grid_constant__ Args a, long long B, long long ntiles
     c.inv_count = inv_count;
     c.ck = MODE != 0 ? ckpt + (long long)blockIdx.x * G::ckpt_floats(a.n) : nullptr;
     __syncthreads();
-    build_pos<R>(c, tid);
+    build_pos<R, NW>(c, tid);
     __syncthreads();
     TS ts;
     for (;;) {
@@ -69,7 +70,7 @@ tnq_ladder2_kernel(const __grid_constant__ Args a, long long B, long long ntiles
         c.b0 = tile * G::S;
         c.gpart = MODE != 0 ? gparts + tile * grad_floats(a.n) : nullptr;
         c.lpart = MODE != 0 ? lparts + tile : nullptr;
-        tile_sweep<R, MODE>(c, ts, tid);
+        tile_sweep<R, NW, MODE>(c, ts, tid);
     }
 }
 
@@ -116,59 +117,73 @@ tnq_l2_finalize_kernel(const __grid_constant__ Args a, const float* __restrict__
 }
 
 struct Plan {
-    int R, grid;
+    int R, NW, grid;
     long long ntiles;
     size_t smem;
 };
 
-int upw_of(int R) { return R == 1 ? 7 : (R == 2 ? 4 : (R == 4 ? 2 : 1)); }
-size_t smem_of(int R, int mode) {
+int upw_of(int R, int NW) { return ((27 + R - 1) / R + NW - 1) / NW; }      // units the busiest warp owns per step
+template <int R, int NW>
+size_t smem_rw(int mode) { return sizeof(float) * (mode == 0 ? Geo<R, NW>::FWD_FLOATS : Geo<R, NW>::TRAIN_FLOATS); }
+size_t smem_of(int R, int NW, int mode) {
+    if (NW == 8) return R == 2 ? smem_rw<2, 8>(mode) : smem_rw<4, 8>(mode);
     switch (R) {
-        case 1: return sizeof(float) * (mode == 0 ? Geo<1>::FWD_FLOATS : Geo<1>::TRAIN_FLOATS);
-        case 2: return sizeof(float) * (mode == 0 ? Geo<2>::FWD_FLOATS : Geo<2>::TRAIN_FLOATS);
-        case 4: return sizeof(float) * (mode == 0 ? Geo<4>::FWD_FLOATS : Geo<4>::TRAIN_FLOATS);
-        default: return sizeof(float) * (mode == 0 ? Geo<8>::FWD_FLOATS : Geo<8>::TRAIN_FLOATS);
+        case 1: return smem_rw<1, 4>(mode);
+        case 2: return smem_rw<2, 4>(mode);
+        case 4: return smem_rw<4, 4>(mode);
+        default: return smem_rw<8, 4>(mode);
     }
 }
 long long ckpt_of(int R, int n) {
     switch (R) {
-        case 1: return Geo<1>::ckpt_floats(n);
-        case 2: return Geo<2>::ckpt_floats(n);
-        case 4: return Geo<4>::ckpt_floats(n);
-        default: return Geo<8>::ckpt_floats(n);
+        case 1: return Geo<1, 4>::ckpt_floats(n);
+        case 2: return Geo<2, 4>::ckpt_floats(n);
+        case 4: return Geo<4, 4>::ckpt_floats(n);
+        default: return Geo<8, 4>::ckpt_floats(n);
     }
 }
 
-// CTAs that fit on one SM: registers (16 K per scheduler partition, one warp of every CTA on each) and shared memory
-int ctas_per_sm(int R, int mode, int smem_sm) {
-    const int by_regs = mode == 0 ? 4 : 2;
-    const int by_smem = (int)((size_t)smem_sm / (smem_of(R, mode) + 1024));
-    return by_smem < by_regs ? (by_smem < 1 ? 1 : by_smem) : by_regs;
+// CTAs that fit on one SM: registers (16 K per scheduler partition; a CTA puts NW / 4 warps on each) and shared memory
+int ctas_per_sm(int R, int NW, int mode, int smem_sm) {
+    const int by_regs = (mode == 0 ? 4 : 2) * 4 / NW;
+    const int by_smem = (int)((size_t)smem_sm / (smem_of(R, NW, mode) + 1024));
+    const int c = by_smem < by_regs ? by_smem : by_regs;
+    return c < 1 ? 1 : c;
 }
 
+// Geometry: tiles of 32 / R samples, NW warps per CTA.  Large batches: 4-warp CTAs, two per SM (training), the tile
+// size that keeps the tail short.  Batches that leave SMs idle at one 4-warp CTA per tile: 8-warp CTAs (R = 2 or 4),
+// half the row blocks per warp, i.e. about half the latency of a tile -- the per-GPU batch of the 8-GPU run.
 Plan make_plan(int n, long long B, int mode, int sms, int smem_sm) {
     (void)n;
     Plan best{};
     double best_cost = 0;
     const char* force = getenv("TNQ_LADDER_R");
-    for (int R = 1; R <= 8; R *= 2) {
-        if (force && atoi(force) != R) continue;
-        if (smem_of(R, mode) + 1024 > (size_t)smem_sm) continue;
-        const int S = 32 / R;
-        const long long ntiles = (B + S - 1) / S;
-        const int slots = sms * ctas_per_sm(R, mode, smem_sm);
-        const double rounds = (double)ntiles / slots;
-        const double eff = R == 1 ? 1.0 : (R == 8 ? 27.0 / 32 : 27.0 / 28);
-        // per-CTA speed when the SM is shared by fewer CTAs than the registers allow is not modelled: favour filling it
-        const double cost = (rounds < 1 ? 1 : rounds) * upw_of(R) / eff / ctas_per_sm(R, mode, smem_sm) * (mode == 0 ? 4 : 2);
-        if (best.R == 0 || cost < best_cost * 0.999) {
-            best_cost = cost;
-            best.R = R;
-            best.ntiles = ntiles;
-            best.grid = (int)(ntiles < slots ? ntiles : slots);
-            best.smem = smem_of(R, mode);
+    const char* force_w = getenv("TNQ_LADDER_WARPS");
+    for (int NW = 4; NW <= 8; NW *= 2)
+        for (int R = 1; R <= 8; R *= 2) {
+            if (NW == 8 && R != 2 && R != 4) continue;
+            if (force && atoi(force) != R) continue;
+            if (force_w && atoi(force_w) != NW) continue;
+            if (smem_of(R, NW, mode) + 1024 > (size_t)smem_sm) continue;
+            const int S = 32 / R;
+            const long long ntiles = (B + S - 1) / S;
+            const int per_sm = ctas_per_sm(R, NW, mode, smem_sm);
+            const int slots = sms * per_sm;
+            const double rounds = (double)ntiles / slots;
+            const double eff = R == 1 ? 1.0 : (R == 8 ? 27.0 / 32 : 27.0 / 28);
+            // time of a tile ~ units of its busiest warp (x CTAs sharing the SM's issue slots), + a fixed part per step
+            const double tile = (upw_of(R, NW) / eff + 1.5) * per_sm;
+            const double cost = (rounds < 1 ? 1 : rounds) * tile;
+            if (best.R == 0 || cost < best_cost * 0.999) {
+                best_cost = cost;
+                best.R = R;
+                best.NW = NW;
+                best.ntiles = ntiles;
+                best.grid = (int)(ntiles < slots ? ntiles : slots);
+                best.smem = smem_of(R, NW, mode);
+            }
         }
-    }
     return best;
 }
 
@@ -205,22 +220,22 @@ Workspace carve(void* base, const Plan& p, int n, int mode) {
     return w;
 }
 
-template <int R, int MODE>
+template <int R, int NW, int MODE>
 int launch_rm(const Args& a, const Plan& p, const Workspace& w, long long B, const float* seed, float* values,
               float log_scale, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(tnq_ladder2_kernel<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    cudaError_t e = cudaFuncSetAttribute(tnq_ladder2_kernel<R, NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(ladder2)");
-    tnq_ladder2_kernel<R, MODE><<<p.grid, NT, p.smem, st>>>(a, B, p.ntiles, seed, values, w.gparts, w.lparts, w.ckpt, w.counter,
+    tnq_ladder2_kernel<R, NW, MODE><<<p.grid, NW * 32, p.smem, st>>>(a, B, p.ntiles, seed, values, w.gparts, w.lparts, w.ckpt, w.counter,
                                                              log_scale, 1.0f / (float)B);
     tnq_internal_count_launch();
     return 0;
 }
-template <int R>
+template <int R, int NW>
 int launch_r(const Args& a, const Plan& p, const Workspace& w, long long B, int mode, const float* seed, float* values,
              float log_scale, cudaStream_t st) {
-    if (mode == 0) return launch_rm<R, 0>(a, p, w, B, seed, values, log_scale, st);
-    if (mode == 1) return launch_rm<R, 1>(a, p, w, B, seed, values, log_scale, st);
-    return launch_rm<R, 2>(a, p, w, B, seed, values, log_scale, st);
+    if (mode == 0) return launch_rm<R, NW, 0>(a, p, w, B, seed, values, log_scale, st);
+    if (mode == 1) return launch_rm<R, NW, 1>(a, p, w, B, seed, values, log_scale, st);
+    return launch_rm<R, NW, 2>(a, p, w, B, seed, values, log_scale, st);
 }
 
 }  // namespace
@@ -235,12 +250,12 @@ int64_t tnq_mps_ladder2_workspace_bytes(int n, int64_t B, int mode) {
     return (int64_t)carve(nullptr, p, n, mode).bytes + 256;
 }
 
-/* geometry the launch would use (tests / bench): out = {R, samples per tile, tiles, grid, dynamic smem bytes} */
+/* geometry the launch would use (tests / bench): out[6] = {R, samples per tile, tiles, grid, dynamic smem bytes, warps per CTA} */
 int tnq_mps_ladder2_geometry(int n, int64_t B, int mode, int64_t* out) {
     int sms, smem_sm;
     device_limits(sms, smem_sm);
     const Plan p = make_plan(n, B, mode, sms, smem_sm);
-    out[0] = p.R, out[1] = 32 / p.R, out[2] = p.ntiles, out[3] = p.grid, out[4] = (int64_t)p.smem;
+    out[0] = p.R, out[1] = 32 / p.R, out[2] = p.ntiles, out[3] = p.grid, out[4] = (int64_t)p.smem, out[5] = p.NW;
     return 0;
 }
 
@@ -283,11 +298,13 @@ int tnq_mps_ladder2(int n, const float* const* cores_a, const float* const* core
     cudaError_t e = cudaMemcpyToSymbolAsync(tnq_l2_cst_dev, w.image, sizeof(float) * nc, 0, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaMemcpyToSymbolAsync(ladder2 constants)");
     int rc;
-    switch (p.R) {
-        case 1: rc = launch_r<1>(a, p, w, B, mode, seed, values, (float)log_scale, st); break;
-        case 2: rc = launch_r<2>(a, p, w, B, mode, seed, values, (float)log_scale, st); break;
-        case 4: rc = launch_r<4>(a, p, w, B, mode, seed, values, (float)log_scale, st); break;
-        default: rc = launch_r<8>(a, p, w, B, mode, seed, values, (float)log_scale, st); break;
+    switch (p.R * 16 + p.NW) {
+        case 1 * 16 + 4: rc = launch_r<1, 4>(a, p, w, B, mode, seed, values, (float)log_scale, st); break;
+        case 2 * 16 + 4: rc = launch_r<2, 4>(a, p, w, B, mode, seed, values, (float)log_scale, st); break;
+        case 4 * 16 + 4: rc = launch_r<4, 4>(a, p, w, B, mode, seed, values, (float)log_scale, st); break;
+        case 8 * 16 + 4: rc = launch_r<8, 4>(a, p, w, B, mode, seed, values, (float)log_scale, st); break;
+        case 2 * 16 + 8: rc = launch_r<2, 8>(a, p, w, B, mode, seed, values, (float)log_scale, st); break;
+        default: rc = launch_r<4, 8>(a, p, w, B, mode, seed, values, (float)log_scale, st); break;
     }
     if (rc) return rc;
     if (mode != 0) {

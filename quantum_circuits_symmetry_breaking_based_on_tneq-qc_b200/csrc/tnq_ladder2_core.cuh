@@ -47,7 +47,7 @@ using tnq_ladder::ldg_f;
 using tnq_ladder::MAXQ;
 
 constexpr int K = 3, K2 = 9, K3 = 27, K4 = 81;
-constexpr int NW = 4, NT = 128;                  // warps / threads per CTA
+// NW warps (4 or 8) per CTA: a template parameter next to R
 
 // ---- constant pool (floats) ------------------------------------------------------------------------
 // one block per step q, then a tail with the extra layouts of the last step and As0
@@ -119,9 +119,10 @@ TNQ_HD float cst_element(const Args& a, int idx) {
 }
 
 // ---- geometry of one variant: R slots x S samples per warp ----------------------------------------------
-template <int R>
+template <int R, int NW>
 struct Geo {
     static_assert(R == 1 || R == 2 || R == 4 || R == 8, "slots per warp");
+    static_assert(NW == 4 || NW == 8, "warps per CTA");
     static constexpr int S = 32 / R;                         // samples per tile
     static constexpr int NU = (K3 + R - 1) / R;              // units (groups of R row blocks) per step
     static constexpr int PO = R == 1 ? 3 : (R == 8 ? 8 : 4);  // padded extent of the o / r position
@@ -137,7 +138,7 @@ struct Geo {
     // training only
     static constexpr int OFF_DT2R = FWD_FLOATS;              // d T2 of the step above, [o''][f''][g] x position of p
     static constexpr int OFF_DT2P = OFF_DT2R + T2_SZ;        // per-thread partial sums of d T2, two flush slots
-    static constexpr int DT2P_SZ = K3 * 2 * NT;
+    static constexpr int DT2P_SZ = K3 * 2 * (NW * 32);
     static constexpr int OFF_DUP = OFF_DT2P + DT2P_SZ;       // per-row-block partial sums of d U
     static constexpr int OFF_P2P = OFF_DUP + T1_SZ;          // per-row-block part 2 of d Bs
     static constexpr int P2P_SZ = K * NU * 32;
@@ -159,7 +160,7 @@ TNQ_HOSTDEV constexpr int grad_floats(int n) { return (n - 1) * GQ; }
 // ---- row blocks: unit u, slot -> rb = o*9 + q'*3 + r (or -1: idle) -----------------------------------
 // Built so that the row blocks of one unit have o / (q',r) / r positions that are pairwise equal or fall
 // into different bank groups (tests/test_ladder2_emu.py checks this exhaustively).
-template <int R>
+template <int R, int NW>
 TNQ_HOSTDEV constexpr int rb_of(int u, int slot) {
     if (R == 1) return u;
     if (R == 2) {
@@ -181,7 +182,7 @@ TNQ_HOSTDEV constexpr int rb_of(int u, int slot) {
     return slot < 3 ? slot * 9 + 8 : -1;
 }
 // inverse: rb -> (unit, slot)
-template <int R>
+template <int R, int NW>
 TNQ_HD void uslot_of(int rb, int& u, int& slot) {
     const int o = rb / 9, qr = rb % 9, qq = qr / 3, r = qr % 3;
     if (R == 1) {
@@ -204,28 +205,27 @@ TNQ_HD void uslot_of(int rb, int& u, int& slot) {
         else u = o, slot = qr;
     }
 }
-template <int R>
+template <int R, int NW>
 TNQ_HD int pos_q(int qr) {                       // position of (q',r) in the U layout
     if (R == 4) return qr == 2 ? 4 : (qr == 3 ? 2 : (qr == 4 ? 3 : qr));
     return qr;
 }
-// units [ustart(w), ustart(w+1)) belong to warp w
-template <int R>
+// units [ustart(w), ustart(w+1)) belong to warp w: NU units dealt as evenly as they go, the first warps one more
+// (4 warps: 7,7,7,6 units at R = 1; 4,4,3,3 at R = 2; 2,2,2,1 at R = 4; 1,1,1,1 at R = 8)
+template <int R, int NW>
 TNQ_HOSTDEV constexpr int ustart(int w) {
-    if (R == 1) return w == 0 ? 0 : (w == 1 ? 7 : (w == 2 ? 14 : (w == 3 ? 21 : 27)));
-    if (R == 2) return w == 0 ? 0 : (w == 1 ? 4 : (w == 2 ? 8 : (w == 3 ? 11 : 14)));
-    if (R == 4) return w == 0 ? 0 : (w == 1 ? 2 : (w == 2 ? 4 : (w == 3 ? 6 : 7)));
-    return w;
+    constexpr int NU = (K3 + R - 1) / R, base = NU / NW, rem = NU % NW;
+    return w * base + (w < rem ? w : rem);
 }
 
 // which o the flush slot fs (0 / 1) of thread group g = warp*R + slot holds after phase_r (-1: unused):
 // a thread parks its running d T2 sum whenever the o of its row blocks changes (at most once, by construction)
-template <int R>
+template <int R, int NW>
 TNQ_HOSTDEV constexpr int flush_o(int g, int fs) {
     const int w = g / R, slot = g % R;
     int cur = -1, n = 0;
-    for (int u = ustart<R>(w); u < ustart<R>(w + 1); ++u) {
-        const int id = rb_of<R>(u, slot);
+    for (int u = ustart<R, NW>(w); u < ustart<R, NW>(w + 1); ++u) {
+        const int id = rb_of<R, NW>(u, slot);
         if (id < 0) continue;
         if (id / 9 != cur) {
             if (cur >= 0) ++n;
@@ -288,12 +288,12 @@ TNQ_HD float load_m(const Ctx& c, int q, long long b, int it) {
 // ================================= forward phases ======================================================
 
 // T2_0 = As0 (x) As0 for every sample of the tile
-template <int R>
+template <int R, int NW>
 TNQ_HD void fill_t2_first(const Ctx& c, int tid) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     float* T2s = c.sm + G::OFF_T2;
     const int base = (c.a->n - 1) * C_STEP + T_AS0;
-    for (int e = tid; e < K4 * G::S; e += NT) {
+    for (int e = tid; e < K4 * G::S; e += (NW * 32)) {
         const int s = e % G::S, x = e / G::S;          // x = ((p*3 + f)*3 + g)*3 + o
         const int o = x % 3, g = (x / 3) % 3, f = (x / 9) % 3, p = x / 27;
         T2s[((p * 9 + f * 3 + g) * G::PO + o) * G::S + s] = TNQ2_CST(base + g * 3 + f) * TNQ2_CST(base + p * 3 + o);
@@ -302,17 +302,17 @@ TNQ_HD void fill_t2_first(const Ctx& c, int tid) {
 
 // phase B: U_q from M_q (task = (i, p, sample); at most two tasks per thread).  The loads of M are split from
 // the arithmetic so that callers can put independent work between them (the loads come from global memory).
-template <int R>
+template <int R, int NW>
 struct UTask {
-    static constexpr int N = (K2 * Geo<R>::S + NT - 1) / NT;   // tasks per thread
+    static constexpr int N = (K2 * Geo<R, NW>::S + (NW * 32) - 1) / (NW * 32);   // tasks per thread
     float m[N][K];
 };
-template <int R>
-TNQ_HD void phase_u_load(const Ctx& c, int q, int tid, UTask<R>& ut) {
-    using G = Geo<R>;
+template <int R, int NW>
+TNQ_HD void phase_u_load(const Ctx& c, int q, int tid, UTask<R, NW>& ut) {
+    using G = Geo<R, NW>;
     TNQ_UNROLL
-    for (int k2 = 0; k2 < UTask<R>::N; ++k2) {
-        const int t = tid + k2 * NT;
+    for (int k2 = 0; k2 < UTask<R, NW>::N; ++k2) {
+        const int t = tid + k2 * (NW * 32);
         if (t < K2 * G::S) {
             const int i = t / G::S / 3, s = t % G::S;
             TNQ_UNROLL
@@ -320,14 +320,14 @@ TNQ_HD void phase_u_load(const Ctx& c, int q, int tid, UTask<R>& ut) {
         }
     }
 }
-template <int R>
-TNQ_HD void phase_u_compute(const Ctx& c, int q, int tid, const UTask<R>& ut) {
-    using G = Geo<R>;
+template <int R, int NW>
+TNQ_HD void phase_u_compute(const Ctx& c, int q, int tid, const UTask<R, NW>& ut) {
+    using G = Geo<R, NW>;
     float* Us = c.sm + G::OFF_U;
     const int cq = q * C_STEP;
     TNQ_UNROLL
-    for (int k2 = 0; k2 < UTask<R>::N; ++k2) {
-        const int t = tid + k2 * NT;
+    for (int k2 = 0; k2 < UTask<R, NW>::N; ++k2) {
+        const int t = tid + k2 * (NW * 32);
         if (t < K2 * G::S) {
             const int ip = t / G::S, s = t % G::S, p = ip % 3;
             Vec<K2> u;
@@ -341,34 +341,34 @@ TNQ_HD void phase_u_compute(const Ctx& c, int q, int tid, const UTask<R>& ut) {
                 for (int qr = 0; qr < K2; ++qr) u.set(qr, fmaf(ut.m[k2][k], TNQ2_CST(row + qr), u.get(qr)));
             }
             TNQ_UNROLL
-            for (int qr = 0; qr < K2; ++qr) Us[(ip * G::PQ + pos_q<R>(qr)) * G::S + s] = u.get(qr);
+            for (int qr = 0; qr < K2; ++qr) Us[(ip * G::PQ + pos_q<R, NW>(qr)) * G::S + s] = u.get(qr);
         }
     }
 }
-template <int R>
+template <int R, int NW>
 TNQ_HD void phase_u(const Ctx& c, int q, int tid) {
-    UTask<R> ut;
-    phase_u_load<R>(c, q, tid, ut);
-    phase_u_compute<R>(c, q, tid, ut);
+    UTask<R, NW> ut;
+    phase_u_load<R, NW>(c, q, tid, ut);
+    phase_u_compute<R, NW>(c, q, tid, ut);
 }
 
 // copy of M_q for the tasks that share it: Ms[(row*3+col)][sample]
-template <int R>
+template <int R, int NW>
 TNQ_HD void load_ms(const Ctx& c, int q, float* Ms, int tid) {
-    using G = Geo<R>;
-    for (int e = tid; e < K2 * G::S; e += NT) Ms[e] = load_m(c, q, c.b0 + e % G::S, e / G::S);
+    using G = Geo<R, NW>;
+    for (int e = tid; e < K2 * G::S; e += (NW * 32)) Ms[e] = load_m(c, q, c.b0 + e % G::S, e / G::S);
 }
 
 // phase A2: T2_q from T1_q (task = (f, p, g, sample)); training keeps a copy in the checkpoint slab
-template <int R, bool CK>
+template <int R, int NW, bool CK>
 TNQ_HD void phase_a2(const Ctx& c, int q, int tid) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     const float* T1s = c.sm + G::OFF_T1;
     float* T2s = c.sm + G::OFF_T2;
     const int* pos = reinterpret_cast<const int*>(c.sm + G::OFF_POS);
     const int cq = q * C_STEP;
     TNQ_NOUNROLL
-    for (int t = tid; t < K3 * G::S; t += NT) {
+    for (int t = tid; t < K3 * G::S; t += (NW * 32)) {
         const int s = t % G::S, x = t / G::S;              // x = (f*3 + p)*3 + g
         const int g = x % 3, p = (x / 3) % 3, f = x / 9;
         Vec<K> acc;
@@ -390,7 +390,7 @@ TNQ_HD void phase_a2(const Ctx& c, int q, int tid) {
 }
 
 // this thread's operands of one row block
-template <int R>
+template <int R, int NW>
 struct RowBlock {
     int o, qr, u;
     const float* t2;            // + ((p'*9 + f*3+g') * PO) * S
@@ -398,23 +398,23 @@ struct RowBlock {
 };
 // (an idle slot -- there is at most one unit with idle slots per step -- computes on row block 0 and drops its
 // results: no divergent control flow inside the hot loops)
-template <int R>
-TNQ_HD bool row_block(const Ctx& c, int u, int lane, RowBlock<R>& rb) {
-    using G = Geo<R>;
+template <int R, int NW>
+TNQ_HD bool row_block(const Ctx& c, int u, int lane, RowBlock<R, NW>& rb) {
+    using G = Geo<R, NW>;
     const int slot = lane / G::S, s = lane % G::S;
-    int id = rb_of<R>(u, slot);
+    int id = rb_of<R, NW>(u, slot);
     const bool active = id >= 0;
     id = active ? id : 0;
     rb.o = id / 9, rb.qr = id % 9, rb.u = u;
     rb.t2 = c.sm + G::OFF_T2 + rb.o * G::S + s;
-    rb.uu = c.sm + G::OFF_U + pos_q<R>(rb.qr) * G::S + s;
+    rb.uu = c.sm + G::OFF_U + pos_q<R, NW>(rb.qr) * G::S + s;
     return active;
 }
 
 // V[i'] over (f,g') = sum_p' T2[f,o,g',p'] U[i',p',q',r]
-template <int R>
-TNQ_HD void make_v(const RowBlock<R>& rb, const float (&u9)[K2], Vec<K2> (&V)[K]) {
-    using G = Geo<R>;
+template <int R, int NW>
+TNQ_HD void make_v(const RowBlock<R, NW>& rb, const float (&u9)[K2], Vec<K2> (&V)[K]) {
+    using G = Geo<R, NW>;
     TNQ_UNROLL
     for (int i = 0; i < K; ++i) V[i].zero();
     TNQ_UNROLL
@@ -442,20 +442,20 @@ TNQ_HD void make_e(const Ctx& c, int cq, const Vec<K2> (&V)[K], Vec<K2> (&E)[K])
 }
 
 // fused phase C of step q and phase A1 of step q+1, one row block (o,q',r) at a time
-template <int R>
+template <int R, int NW>
 TNQ_HD void phase_c_a1(const Ctx& c, int q, int warp, int lane) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     float* T1s = c.sm + G::OFF_T1;
     const int cq = q * C_STEP, cq1 = (q + 1) * C_STEP;
     TNQ_NOUNROLL
-    for (int u = ustart<R>(warp); u < ustart<R>(warp + 1); ++u) {
-        RowBlock<R> rb;
-        const bool active = row_block<R>(c, u, lane, rb);
+    for (int u = ustart<R, NW>(warp); u < ustart<R, NW>(warp + 1); ++u) {
+        RowBlock<R, NW> rb;
+        const bool active = row_block<R, NW>(c, u, lane, rb);
         float u9[K2];
         TNQ_UNROLL
         for (int x = 0; x < K2; ++x) u9[x] = rb.uu[x * G::PQ * G::S];
         Vec<K2> V[K], E[K];
-        make_v<R>(rb, u9, V);
+        make_v<R, NW>(rb, u9, V);
         make_e(c, cq, V, E);
         Vec<K> T1[K];                      // [j] over f''
         TNQ_UNROLL
@@ -477,9 +477,9 @@ TNQ_HD void phase_c_a1(const Ctx& c, int q, int warp, int lane) {
 }
 
 // last step, shared by the forward and the reverse pass: L[j][p'] and Z over (p0,o) of task (g,f)
-template <int R>
+template <int R, int NW>
 TNQ_HD void last_lz(const Ctx& c, int gf, int s, float (&mh)[K][K], float (&mi)[K][K], float (&L)[K][K], Vec<K2>& Z) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     const int n = c.a->n;
     const float* MA = c.sm + G::OFF_MA;
     const float* MB = c.sm + G::OFF_MB;
@@ -521,17 +521,17 @@ TNQ_HD void last_lz(const Ctx& c, int gf, int s, float (&mh)[K][K], float (&mi)[
     }
 }
 
-template <int R>
+template <int R, int NW>
 TNQ_HD void last_fwd(const Ctx& c, int tid) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     const float* T2s = c.sm + G::OFF_T2;
     float* valp = c.sm + G::OFF_VAL;
     TNQ_NOUNROLL
-    for (int t = tid; t < K2 * G::S; t += NT) {
+    for (int t = tid; t < K2 * G::S; t += (NW * 32)) {
         const int gf = t / G::S, s = t % G::S, g = gf / 3, f = gf % 3;
         float mh[K][K], mi[K][K], L[K][K];
         Vec<K2> Z;
-        last_lz<R>(c, gf, s, mh, mi, L, Z);
+        last_lz<R, NW>(c, gf, s, mh, mi, L, Z);
         float v = 0.f;
         TNQ_UNROLL
         for (int po = 0; po < K2; ++po)
@@ -541,9 +541,9 @@ TNQ_HD void last_fwd(const Ctx& c, int tid) {
 }
 
 // value, loss and d loss / d value of the tile's samples (MODE 0: values only)
-template <int R, int MODE>
+template <int R, int NW, int MODE>
 TNQ_HD void last_value(const Ctx& c, int tid) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     if (tid >= G::S) return;
     float* valp = c.sm + G::OFF_VAL;
     float val = 0.f;
@@ -569,9 +569,9 @@ TNQ_HD void last_value(const Ctx& c, int tid) {
 // ================================= reverse phases ======================================================
 
 // reverse of the last step (task = (g,f,sample)): d T2 (complete), d X of both copies
-template <int R>
+template <int R, int NW>
 TNQ_HD void last_bwd(const Ctx& c, TS& ts, int tid) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     const int n = c.a->n;
     const float* T2s = c.sm + G::OFF_T2;
     float* dT2r = c.sm + G::OFF_DT2R;
@@ -583,11 +583,11 @@ TNQ_HD void last_bwd(const Ctx& c, TS& ts, int tid) {
     for (int x = 0; x < K2; ++x) ts.accB[x].zero();
     const int tail = (n - 1) * C_STEP;
     TNQ_NOUNROLL
-    for (int t = tid; t < K2 * G::S; t += NT) {
+    for (int t = tid; t < K2 * G::S; t += (NW * 32)) {
         const int gf = t / G::S, s = t % G::S, g = gf / 3, f = gf % 3;
         float mh[K][K], mi[K][K], L[K][K];
         Vec<K2> Z;
-        last_lz<R>(c, gf, s, mh, mi, L, Z);
+        last_lz<R, NW>(c, gf, s, mh, mi, L, Z);
         const float dv = dval[s];
         Vec<K2> Lv, dL;
         TNQ_UNROLL
@@ -626,9 +626,9 @@ TNQ_HD void last_bwd(const Ctx& c, TS& ts, int tid) {
 }
 
 // flush scratch of warp `warp`: rows [27*ROUND, 27*ROUND+27) of this lane's accumulators
-template <int R, int ROUND>
+template <int R, int NW, int ROUND>
 TNQ_HD void flush_put(const Ctx& c, const TS& ts, int warp, int lane) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     float* buf = c.sm + G::OFF_FL + warp * (K3 * 33);
     TNQ_UNROLL
     for (int r = 0; r < K3; ++r) {
@@ -636,9 +636,9 @@ TNQ_HD void flush_put(const Ctx& c, const TS& ts, int warp, int lane) {
         else buf[r * 33 + lane] = ts.accB[r / 3].get(r % 3);
     }
 }
-template <int R>
+template <int R, int NW>
 TNQ_HD void flush_sum(const Ctx& c, int round, int warp, int lane) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     if (lane >= K3) return;
     const float* buf = c.sm + G::OFF_FL + warp * (K3 * 33) + lane * 33;
     float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;         // (fixed association: deterministic)
@@ -648,20 +648,20 @@ TNQ_HD void flush_sum(const Ctx& c, int round, int warp, int lane) {
 }
 
 // row block -> position of its lane run in the row-block-indexed buffers (unit*32 + slot*S): once per CTA
-template <int R>
+template <int R, int NW>
 TNQ_HD void build_pos(const Ctx& c, int tid) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     if (tid >= K3) return;
     int u, slot;
-    uslot_of<R>(tid, u, slot);
+    uslot_of<R, NW>(tid, u, slot);
     reinterpret_cast<int*>(c.sm + G::OFF_POS)[tid] = u * 32 + slot * G::S;
 }
 
 // reverse of the fused phase (row block (o,q',r)): from d T1_{q+1}, d T2_{q+1}, T2_q, U_q
 //   E' (recomputed), d Bs_{q+1} (both parts), d E', d X_q (left copy), d V, d T2_q and d U_q partial sums
-template <int R>
+template <int R, int NW>
 TNQ_HD void phase_r(const Ctx& c, TS& ts, int q, int warp, int lane) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     const float* dT1s = c.sm + G::OFF_T1;
     const float* dT2r = c.sm + G::OFF_DT2R;
     float* dT2p = c.sm + G::OFF_DT2P;
@@ -678,13 +678,13 @@ TNQ_HD void phase_r(const Ctx& c, TS& ts, int q, int warp, int lane) {
     for (int p = 0; p < K; ++p) dT2acc[p].zero();
     int cur_o = -1, fs = 0;
     TNQ_NOUNROLL
-    for (int u = ustart<R>(warp); u < ustart<R>(warp + 1); ++u) {
-        RowBlock<R> rb;
-        const bool active = row_block<R>(c, u, lane, rb);
+    for (int u = ustart<R, NW>(warp); u < ustart<R, NW>(warp + 1); ++u) {
+        RowBlock<R, NW> rb;
+        const bool active = row_block<R, NW>(c, u, lane, rb);
         if (active && rb.o != cur_o) {      // the running d T2 sum belongs to another o: park it
             if (cur_o >= 0) {
                 TNQ_UNROLL
-                for (int x = 0; x < K3; ++x) dT2p[(x * 2 + fs) * NT + tid] = dT2acc[x / 9].get(x % 9);
+                for (int x = 0; x < K3; ++x) dT2p[(x * 2 + fs) * (NW * 32) + tid] = dT2acc[x / 9].get(x % 9);
                 TNQ_UNROLL
                 for (int p = 0; p < K; ++p) dT2acc[p].zero();
                 ++fs;
@@ -700,7 +700,7 @@ TNQ_HD void phase_r(const Ctx& c, TS& ts, int q, int warp, int lane) {
             TNQ_UNROLL
             for (int f2 = 0; f2 < K; ++f2) d1[j].set(f2, active ? dT1s[((f2 * 3 + j) * G::NU + u) * 32 + lane] : 0.f);
         Vec<K2> V[K];
-        make_v<R>(rb, u9, V);
+        make_v<R, NW>(rb, u9, V);
         {   // E' -> d Bs part 1, T1 (recomputed) -> d Bs part 2
             Vec<K2> E[K];
             make_e(c, cq, V, E);
@@ -778,14 +778,14 @@ TNQ_HD void phase_r(const Ctx& c, TS& ts, int q, int warp, int lane) {
     }
     if (cur_o >= 0) {
         TNQ_UNROLL
-        for (int x = 0; x < K3; ++x) dT2p[(x * 2 + fs) * NT + tid] = dT2acc[x / 9].get(x % 9);
+        for (int x = 0; x < K3; ++x) dT2p[(x * 2 + fs) * (NW * 32) + tid] = dT2acc[x / 9].get(x % 9);
     }
 }
 
 // sum of per-sample rows [nrows][SP] (starting at row0 of the row buffer) over the samples -> gradient slice
-template <int R>
+template <int R, int NW>
 TNQ_HD void rows_to_grad(const Ctx& c, float* dst, int row0, int nrows, int tid) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     if (tid >= nrows) return;
     const float* rows = c.sm + G::OFF_ROWS + (row0 + tid) * G::SP;
     float t0 = 0.f, t1 = 0.f;
@@ -796,30 +796,30 @@ TNQ_HD void rows_to_grad(const Ctx& c, float* dst, int row0, int nrows, int tid)
 // operands of phase_r(q): T2_q (checkpoint, or As0 (x) As0 for q = 0), U_q, and M_q in the buffer of q's parity.
 // prepare_r_issue starts the global loads (the checkpoint travels with cp.async on the device); prepare_r_finish
 // does the arithmetic and waits for the copy: callers put independent work between the two.
-template <int R>
-TNQ_HD void prepare_r_issue(const Ctx& c, int q, int tid, UTask<R>& ut) {
-    using G = Geo<R>;
+template <int R, int NW>
+TNQ_HD void prepare_r_issue(const Ctx& c, int q, int tid, UTask<R, NW>& ut) {
+    using G = Geo<R, NW>;
     if (q >= 1) {
         float* T2s = c.sm + G::OFF_T2;
         const float* ck = c.ck + (long long)(q - 1) * G::T2_SZ;
         static_assert(G::T2_SZ % 4 == 0, "16-byte units");
 #ifdef __CUDA_ARCH__
         const uint32_t d = (uint32_t)__cvta_generic_to_shared(T2s);
-        for (int e = tid; e < G::T2_SZ / 4; e += NT)
+        for (int e = tid; e < G::T2_SZ / 4; e += (NW * 32))
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * e), "l"(ck + 4 * e) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
 #else
-        for (int e = tid; e < G::T2_SZ; e += NT) T2s[e] = ck[e];
+        for (int e = tid; e < G::T2_SZ; e += (NW * 32)) T2s[e] = ck[e];
 #endif
     }
-    phase_u_load<R>(c, q, tid, ut);
+    phase_u_load<R, NW>(c, q, tid, ut);
 }
-template <int R>
-TNQ_HD void prepare_r_finish(const Ctx& c, int q, int tid, const UTask<R>& ut) {
-    using G = Geo<R>;
-    if (q == 0) fill_t2_first<R>(c, tid);
-    phase_u_compute<R>(c, q, tid, ut);
-    load_ms<R>(c, q, c.sm + ((q & 1) ? G::OFF_MB : G::OFF_MA), tid);
+template <int R, int NW>
+TNQ_HD void prepare_r_finish(const Ctx& c, int q, int tid, const UTask<R, NW>& ut) {
+    using G = Geo<R, NW>;
+    if (q == 0) fill_t2_first<R, NW>(c, tid);
+    phase_u_compute<R, NW>(c, q, tid, ut);
+    load_ms<R, NW>(c, q, c.sm + ((q & 1) ? G::OFF_MB : G::OFF_MA), tid);
 #ifdef __CUDA_ARCH__
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
@@ -833,16 +833,17 @@ TNQ_HD void prepare_r_finish(const Ctx& c, int q, int tid, const UTask<R>& ut) {
 //     reads it, and in the same task d T1_q = A2^T(d T2_q)                     (task = (p, f, g, sample))
 //   * d U_q = sum over o of the partial sums, right-copy d X_q per sample -> row buffer (finished by finish_prev)
 //   * the operands of phase_r(q-1)
-template <int R>
+template <int R, int NW>
 TNQ_HD void phase_x(const Ctx& c, int q, bool after_r, int tid) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     const float* ws = c.sm + G::OFF_WS;
     const int* pos = reinterpret_cast<const int*>(c.sm + G::OFF_POS);
     float* gq = c.gpart + (long long)q * GQ;
-    UTask<R> ut;
-    if (q >= 1) prepare_r_issue<R>(c, q - 1, tid, ut);
+    UTask<R, NW> ut;
+    if (q >= 1) prepare_r_issue<R, NW>(c, q - 1, tid, ut);
     if (tid < 108) {
-        const float t = (ws[tid] + ws[108 + tid]) + (ws[216 + tid] + ws[324 + tid]);
+        float t = (ws[tid] + ws[108 + tid]) + (ws[216 + tid] + ws[324 + tid]);
+        if (NW == 8) t += (ws[432 + tid] + ws[540 + tid]) + (ws[648 + tid] + ws[756 + tid]);
         if (!after_r) {
             if (tid < K4) gq[K4 + tid] = t;
         } else if (tid < K4) {
@@ -852,7 +853,7 @@ TNQ_HD void phase_x(const Ctx& c, int q, bool after_r, int tid) {
             gq[GQ + 162 + tid - K4] = t;                    // d Bs_{q+1} part 1, natural (c,e,f)
         }
     }
-    if (!after_r) rows_to_grad<R>(c, gq, 0, K4, tid);       // left-copy rows of the last step
+    if (!after_r) rows_to_grad<R, NW>(c, gq, 0, K4, tid);       // left-copy rows of the last step
     if (after_r && tid < 108) {
         // d Bs_{q+1} part 2: [(l,n)][o''] = sum over p and the samples; here: four quarter sums per entry
         const int row = tid >> 2, part = tid & 3, ln = row / 3, o2 = row % 3;
@@ -871,7 +872,7 @@ TNQ_HD void phase_x(const Ctx& c, int q, bool after_r, int tid) {
         float* dT1s = c.sm + G::OFF_T1;
         const int cq = q * C_STEP;
         TNQ_NOUNROLL
-        for (int t = tid; t < K3 * G::S; t += NT) {
+        for (int t = tid; t < K3 * G::S; t += (NW * 32)) {
             const int s = t % G::S, x = t / G::S, p = x / 9, fg = x % 9;    // x = p*9 + f*3 + g
             float d[K] = {0.f, 0.f, 0.f};
             if (after_r) {
@@ -879,8 +880,8 @@ TNQ_HD void phase_x(const Ctx& c, int q, bool after_r, int tid) {
                 for (int g = 0; g < NW * R; ++g)
                     TNQ_UNROLL
                     for (int fs = 0; fs < 2; ++fs) {
-                        const int o = flush_o<R>(g, fs);    // (compile time after unrolling)
-                        if (o >= 0) d[o] += dT2p[(x * 2 + fs) * NT + (g / R) * 32 + (g % R) * G::S + s];
+                        const int o = flush_o<R, NW>(g, fs);    // (compile time after unrolling)
+                        if (o >= 0) d[o] += dT2p[(x * 2 + fs) * (NW * 32) + (g / R) * 32 + (g % R) * G::S + s];
                     }
                 TNQ_UNROLL
                 for (int o = 0; o < K; ++o) dT2r[((o * 9 + fg) * G::PO + p) * G::S + s] = d[o];
@@ -908,7 +909,7 @@ TNQ_HD void phase_x(const Ctx& c, int q, bool after_r, int tid) {
         const float* Mq = c.sm + ((q & 1) ? G::OFF_MB : G::OFF_MA);
         float* rows = c.sm + G::OFF_ROWS;
         TNQ_NOUNROLL
-        for (int t = tid; t < K3 * G::S; t += NT) {
+        for (int t = tid; t < K3 * G::S; t += (NW * 32)) {
             const int s = t % G::S, e = t / G::S, p = e / 9, qr = e % 9;    // e = p'*9 + qr
             const int a0 = pos[qr] + s, a1 = pos[9 + qr] + s, a2 = pos[18 + qr] + s;
             float du[K];
@@ -926,15 +927,15 @@ TNQ_HD void phase_x(const Ctx& c, int q, bool after_r, int tid) {
             }
         }
     }
-    if (q >= 1) prepare_r_finish<R>(c, q - 1, tid, ut);
+    if (q >= 1) prepare_r_finish<R, NW>(c, q - 1, tid, ut);
 }
 
 // what phase X(q) left unfinished (run one barrier later): right-copy d X_q rows and d Bs_{q+1} part 2 -> gradient slice
-template <int R>
+template <int R, int NW>
 TNQ_HD void finish_prev(const Ctx& c, int q, int tid) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     // (given to the LAST warps: they own one row block less in the phase_r that follows)
-    rows_to_grad<R>(c, c.gpart + (long long)q * GQ + K4, 0, K4, NT - 1 - tid);
+    rows_to_grad<R, NW>(c, c.gpart + (long long)q * GQ + K4, 0, K4, (NW * 32) - 1 - tid);
     if (tid < K3) {
         const float* qs = c.sm + G::OFF_WS + NW * 108 + tid * 4;
         c.gpart[(long long)(q + 1) * GQ + 189 + tid] = (qs[0] + qs[1]) + (qs[2] + qs[3]);
@@ -942,14 +943,14 @@ TNQ_HD void finish_prev(const Ctx& c, int q, int tid) {
 }
 
 // first step: d As0[e][f'] = sum_{p,o} d T2_0[f',o,e,p] As0[p][o] + sum_{g,f} d T2_0[f,f',g,e] As0[g][f], per sample
-template <int R>
+template <int R, int NW>
 TNQ_HD void das0_rows(const Ctx& c, int tid) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     const float* dT2r = c.sm + G::OFF_DT2R;
     float* rows = c.sm + G::OFF_ROWS + K4 * G::SP;
     const int base = (c.a->n - 1) * C_STEP + T_AS0;
     TNQ_NOUNROLL
-    for (int t = tid; t < K2 * G::S; t += NT) {
+    for (int t = tid; t < K2 * G::S; t += (NW * 32)) {
         const int s = t % G::S, ef = t / G::S, e = ef / 3, f1 = ef % 3;
         float v = 0.f;
         for (int a1 = 0; a1 < K; ++a1)
@@ -979,7 +980,7 @@ TNQ_HD void das0_rows(const Ctx& c, int tid) {
 #define TNQ2_THREAD_PARAM TS &ts, const int tid
 #else
 #define TNQ2_PH(...)                        \
-    for (int tid = 0; tid < NT; ++tid) {    \
+    for (int tid = 0; tid < (NW * 32); ++tid) {    \
         TS& ts = tss[tid];                  \
         (void)ts;                           \
         __VA_ARGS__                         \
@@ -991,28 +992,28 @@ TNQ_HD void das0_rows(const Ctx& c, int tid) {
 namespace tnq_l2 {
 
 // MODE 0: values.  MODE 1: values + fused loss + gradients.  MODE 2: gradients seeded by c.seed.
-template <int R, int MODE>
+template <int R, int NW, int MODE>
 TNQ_HD void tile_sweep(const Ctx& c, TNQ2_THREAD_PARAM) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
     const int n = c.a->n;
     constexpr bool CK = MODE != 0;
 #define TNQ2_WARP (tid >> 5)
 #define TNQ2_LANE (tid & 31)
     // ------------------------------- forward sweep -------------------------------
-    TNQ2_PH(fill_t2_first<R>(c, tid); phase_u<R>(c, 0, tid);)
+    TNQ2_PH(fill_t2_first<R, NW>(c, tid); phase_u<R, NW>(c, 0, tid);)
     for (int q = 0; q <= n - 3; ++q) {
-        TNQ2_PH(phase_c_a1<R>(c, q, TNQ2_WARP, TNQ2_LANE);)
+        TNQ2_PH(phase_c_a1<R, NW>(c, q, TNQ2_WARP, TNQ2_LANE);)
         TNQ2_PH(
-            phase_a2<R, CK>(c, q + 1, tid);
+            phase_a2<R, NW, CK>(c, q + 1, tid);
             if (q + 1 <= n - 3) {
-                phase_u<R>(c, q + 1, tid);
+                phase_u<R, NW>(c, q + 1, tid);
             } else {
-                load_ms<R>(c, n - 2, c.sm + G::OFF_MA, tid);
-                load_ms<R>(c, n - 1, c.sm + G::OFF_MB, tid);
+                load_ms<R, NW>(c, n - 2, c.sm + G::OFF_MA, tid);
+                load_ms<R, NW>(c, n - 1, c.sm + G::OFF_MB, tid);
             })
     }
-    TNQ2_PH(last_fwd<R>(c, tid);)
-    TNQ2_PH(last_value<R, MODE>(c, tid);)
+    TNQ2_PH(last_fwd<R, NW>(c, tid);)
+    TNQ2_PH(last_value<R, NW, MODE>(c, tid);)
     if (MODE == 0) return;
     // ------------------------------- reverse sweep -------------------------------
     TNQ2_PHW(
@@ -1021,29 +1022,29 @@ TNQ_HD void tile_sweep(const Ctx& c, TNQ2_THREAD_PARAM) {
             for (int s = 0; s < G::S; ++s) t += c.sm[G::OFF_VAL + K2 * G::S + s];
             *c.lpart = t;
         }
-        last_bwd<R>(c, ts, tid);)
+        last_bwd<R, NW>(c, ts, tid);)
 #define TNQ2_FLUSH(ROUND)                                                  \
-    TNQ2_PHW(flush_put<R, ROUND>(c, ts, TNQ2_WARP, TNQ2_LANE);)             \
-    TNQ2_PHW(flush_sum<R>(c, ROUND, TNQ2_WARP, TNQ2_LANE);)
+    TNQ2_PHW(flush_put<R, NW, ROUND>(c, ts, TNQ2_WARP, TNQ2_LANE);)             \
+    TNQ2_PHW(flush_sum<R, NW>(c, ROUND, TNQ2_WARP, TNQ2_LANE);)
 #define TNQ2_FLUSH_LAST(ROUND)                                             \
-    TNQ2_PHW(flush_put<R, ROUND>(c, ts, TNQ2_WARP, TNQ2_LANE);)             \
-    TNQ2_PH(flush_sum<R>(c, ROUND, TNQ2_WARP, TNQ2_LANE);)
+    TNQ2_PHW(flush_put<R, NW, ROUND>(c, ts, TNQ2_WARP, TNQ2_LANE);)             \
+    TNQ2_PH(flush_sum<R, NW>(c, ROUND, TNQ2_WARP, TNQ2_LANE);)
     TNQ2_FLUSH(0)
     TNQ2_FLUSH(1)
     TNQ2_FLUSH_LAST(2)
-    TNQ2_PH(phase_x<R>(c, n - 2, false, tid);)
+    TNQ2_PH(phase_x<R, NW>(c, n - 2, false, tid);)
     for (int q = n - 3; q >= 0; --q) {
         TNQ2_PHW(
-            if (q < n - 3) finish_prev<R>(c, q + 1, tid);
-            phase_r<R>(c, ts, q, TNQ2_WARP, TNQ2_LANE);)
+            if (q < n - 3) finish_prev<R, NW>(c, q + 1, tid);
+            phase_r<R, NW>(c, ts, q, TNQ2_WARP, TNQ2_LANE);)
         TNQ2_FLUSH(0)
         TNQ2_FLUSH(1)
         TNQ2_FLUSH(2)
         TNQ2_FLUSH_LAST(3)
-        TNQ2_PH(phase_x<R>(c, q, true, tid);)
+        TNQ2_PH(phase_x<R, NW>(c, q, true, tid);)
     }
-    TNQ2_PH(finish_prev<R>(c, 0, tid); das0_rows<R>(c, tid);)
-    TNQ2_PH(rows_to_grad<R>(c, c.gpart + 162, K4, K2, tid);)
+    TNQ2_PH(finish_prev<R, NW>(c, 0, tid); das0_rows<R, NW>(c, tid);)
+    TNQ2_PH(rows_to_grad<R, NW>(c, c.gpart + 162, K4, K2, tid);)
 #undef TNQ2_FLUSH_LAST
 #undef TNQ2_FLUSH
 #undef TNQ2_WARP

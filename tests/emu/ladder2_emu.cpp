@@ -12,9 +12,10 @@
 
 using namespace tnq_l2;
 
-template <int R, int MODE>
+template <int R, int NW, int MODE>
 static void run(const Args& a, long long B, const float* seed, float* values, float* loss, double log_scale) {
-    using G = Geo<R>;
+    using G = Geo<R, NW>;
+    constexpr int NT = NW * 32;
     const int n = a.n;
     std::vector<float> cst(cst_floats(n));
     for (int i = 0; i < cst_floats(n); ++i) cst[i] = cst_element(a, i);
@@ -33,12 +34,12 @@ static void run(const Args& a, long long B, const float* seed, float* values, fl
     c.inv_count = 1.0f / (float)B;
     c.ck = ck.data();
     std::vector<TS> tss(NT);
-    for (int tid = 0; tid < NT; ++tid) build_pos<R>(c, tid);
+    for (int tid = 0; tid < NT; ++tid) build_pos<R, NW>(c, tid);
     for (long long tile = 0; tile < ntiles; ++tile) {
         c.b0 = tile * G::S;
         c.gpart = gparts.data() + (size_t)tile * ng;
         c.lpart = lparts.data() + tile;
-        tile_sweep<R, MODE>(c, tss.data());
+        tile_sweep<R, NW, MODE>(c, tss.data());
     }
     if (MODE == 0) return;
     for (int q = 0; q < n - 1; ++q)
@@ -53,14 +54,15 @@ static void run(const Args& a, long long B, const float* seed, float* values, fl
     }
 }
 
-template <int R>
+template <int R, int NW>
 static void run_r(const Args& a, long long B, int mode, const float* seed, float* values, float* loss, double ls) {
-    if (mode == 0) run<R, 0>(a, B, seed, values, loss, ls);
-    else if (mode == 1) run<R, 1>(a, B, seed, values, loss, ls);
-    else run<R, 2>(a, B, seed, values, loss, ls);
+    if (mode == 0) run<R, NW, 0>(a, B, seed, values, loss, ls);
+    else if (mode == 1) run<R, NW, 1>(a, B, seed, values, loss, ls);
+    else run<R, NW, 2>(a, B, seed, values, loss, ls);
 }
 
-extern "C" int ladder2_emu(int R, int n, const float* const* coreA, const float* const* coreX, const float* const* states,
+// R: slots per warp; warps: 4 or 8 warps per CTA
+extern "C" int ladder2_emu(int R, int warps, int n, const float* const* coreA, const float* const* coreX, const float* const* states,
                            const float* const* mx, const long long* mx_stride, long long B, int mode, const float* seed,
                            float* values, float* loss, float* const* gradA, float* const* gradX, double log_scale) {
     if (n < 3 || n > MAXQ || mode < 0 || mode > 2) return 1;
@@ -78,11 +80,14 @@ extern "C" int ladder2_emu(int R, int n, const float* const* coreA, const float*
         a.gradA[q] = gradA ? gradA[q] : nullptr;
         a.gradX[q] = gradX ? gradX[q] : nullptr;
     }
-    switch (R) {
-        case 1: run_r<1>(a, B, mode, seed, values, loss, log_scale); break;
-        case 2: run_r<2>(a, B, mode, seed, values, loss, log_scale); break;
-        case 4: run_r<4>(a, B, mode, seed, values, loss, log_scale); break;
-        case 8: run_r<8>(a, B, mode, seed, values, loss, log_scale); break;
+    if (warps != 4 && warps != 8) return 3;
+    switch (R * 16 + warps) {
+        case 1 * 16 + 4: run_r<1, 4>(a, B, mode, seed, values, loss, log_scale); break;
+        case 2 * 16 + 4: run_r<2, 4>(a, B, mode, seed, values, loss, log_scale); break;
+        case 4 * 16 + 4: run_r<4, 4>(a, B, mode, seed, values, loss, log_scale); break;
+        case 8 * 16 + 4: run_r<8, 4>(a, B, mode, seed, values, loss, log_scale); break;
+        case 2 * 16 + 8: run_r<2, 8>(a, B, mode, seed, values, loss, log_scale); break;
+        case 4 * 16 + 8: run_r<4, 8>(a, B, mode, seed, values, loss, log_scale); break;
         default: return 2;
     }
     return 0;
@@ -92,20 +97,21 @@ extern "C" int ladder2_emu(int R, int n, const float* const* coreA, const float*
 // of the row blocks of one unit are pairwise equal or distinct modulo R, for o, (q',r) and r)
 template <int R>
 static int check_tables() {
-    using G = Geo<R>;
+    constexpr int NW = 4;
+    using G = Geo<R, NW>;
     int seen[27] = {0};
     for (int u = 0; u < G::NU; ++u) {
         int po[8], pq[8], pr[8], cnt = 0;
         for (int slot = 0; slot < R; ++slot) {
-            const int rb = rb_of<R>(u, slot);
+            const int rb = rb_of<R, NW>(u, slot);
             if (rb < 0) continue;
             if (rb >= 27) return 1;
             ++seen[rb];
             int uu, ss;
-            uslot_of<R>(rb, uu, ss);
+            uslot_of<R, NW>(rb, uu, ss);
             if (uu != u || ss != slot) return 2;
-            po[cnt] = rb / 9, pq[cnt] = pos_q<R>(rb % 9), pr[cnt] = rb % 3, ++cnt;
-            if (pos_q<R>(rb % 9) >= G::PQ || rb / 9 >= G::PO) return 3;
+            po[cnt] = rb / 9, pq[cnt] = pos_q<R, NW>(rb % 9), pr[cnt] = rb % 3, ++cnt;
+            if (pos_q<R, NW>(rb % 9) >= G::PQ || rb / 9 >= G::PO) return 3;
         }
         for (int i = 0; i < cnt; ++i)
             for (int j = i + 1; j < cnt; ++j) {
@@ -119,8 +125,8 @@ static int check_tables() {
     // positions of (q',r) are a permutation of distinct values
     int used[16] = {0};
     for (int qr = 0; qr < 9; ++qr)
-        if (used[pos_q<R>(qr)]++) return 8;
-    if (ustart<R>(0) != 0 || ustart<R>(NW) != G::NU) return 9;
+        if (used[pos_q<R, NW>(qr)]++) return 8;
+    if (ustart<R, NW>(0) != 0 || ustart<R, NW>(NW) != G::NU) return 9;
     return 0;
 }
 extern "C" int ladder2_check_tables(int R) {

@@ -37,7 +37,7 @@ def emu2(tmp_path_factory):
     return ctypes.CDLL(so)
 
 
-def run_emu2(lib, R, n, cores, layer1, layer2, states, ms, B, mode, seed=None, log_scale=0.0, strides=None):
+def run_emu2(lib, R, n, cores, layer1, layer2, states, ms, B, mode, seed=None, log_scale=0.0, strides=None, warps=4):
     K = 3
     arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
     ca = [cores[k].contiguous() for k in layer1]
@@ -46,7 +46,7 @@ def run_emu2(lib, R, n, cores, layer1, layer2, states, ms, B, mode, seed=None, l
     vals, loss = torch.zeros(B), torch.zeros(1)
     sd = seed if seed is not None else torch.zeros(B)
     st = (ctypes.c_longlong * n)(*(strides or [K * K] * n))
-    rc = lib.ladder2_emu(R, n, arr(ca), arr(cx), arr(states), arr(ms), st, ctypes.c_longlong(B), mode,
+    rc = lib.ladder2_emu(R, warps, n, arr(ca), arr(cx), arr(states), arr(ms), st, ctypes.c_longlong(B), mode,
                          ctypes.c_void_p(sd.data_ptr()), ctypes.c_void_p(vals.data_ptr()),
                          ctypes.c_void_p(loss.data_ptr()), arr(ga), arr(gx), ctypes.c_double(log_scale))
     assert rc == 0
@@ -111,6 +111,23 @@ def test_emulated_kernel_matches_reference_fixture(emu2):
         assert abs(loss.item() - float(c["loss"])) <= 1e-5 * abs(float(c["loss"]))
         for name, w in zip(c["names"], c["grads"]):
             assert (grads[name] - w).abs().max() <= 5e-3 * w.abs().max()
+
+
+@pytest.mark.parametrize("R,n,B", [(2, 5, 21), (4, 6, 11), (2, 3, 7)])
+def test_eight_warp_variant_matches_four_warp_variant(emu2, R, n, B):
+    """The small-batch geometry (8 warps per CTA: half the row blocks per warp) computes what the 4-warp CTA
+    computes: values bit-identical, gradients equal up to the order of the partial sums."""
+    K = 3
+    graph = merged_graph(n, K)
+    _, layer1, layer2 = ladder_of(graph, K)
+    names, table, nq, cores, states, mxs = well_conditioned_case(graph, K, B, "float32", seed=n)
+    raw = [m.tensor.contiguous() for m in mxs]
+    v4, l4, g4 = run_emu2(emu2, R, n, cores, layer1, layer2, states, raw, B, 1, warps=4)
+    v8, l8, g8 = run_emu2(emu2, R, n, cores, layer1, layer2, states, raw, B, 1, warps=8)
+    assert torch.equal(v4, v8)
+    assert abs(l4.item() - l8.item()) <= 1e-6 * abs(l4.item())
+    for k in names:
+        assert (g4[k] - g8[k]).abs().max() <= 2e-5 * g4[k].abs().max() + 1e-12
 
 
 def test_geometries_agree_and_ragged_batches(emu2):

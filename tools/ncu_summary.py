@@ -39,8 +39,14 @@ def main():
     print(title)
     rows = page(rep, "raw")
     hdr, units = rows[0], rows[1]
+    seen = {}
     for r in rows[2:]:
         kern = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        grid = r[hdr.index("launch__grid_size")] if "launch__grid_size" in hdr else ""
+        if (kern, grid) in seen:            # repeated launches of the same kernel and grid: the first one stands
+            seen[(kern, grid)] += 1
+            continue
+        seen[(kern, grid)] = 1
         print(f"\n== {kern}")
         for i, h in enumerate(hdr):
             stall = "issue_stalled" in h and h.endswith("per_issue_active.ratio")
@@ -51,6 +57,8 @@ def main():
         h = {k: i for i, k in enumerate(src[1])}
         by = collections.defaultdict(lambda: [0, 0, 0])
         for r in src[2:]:
+            if len(r) <= max(h["Instructions Executed"], h["# Samples"], h["L1 Wavefronts Shared"]) or not r[h["Instructions Executed"]].strip().isdigit():
+                continue                    # (header lines of further kernels in a multi-kernel report)
             m = re.match(r"\s*(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", r[1])
             op = m.group(1) if m else "?"
             if op in ("LDS", "STS", "LDG", "STG"):
@@ -60,7 +68,7 @@ def main():
             by[op][2] += int(r[h["L1 Wavefronts Shared"]] or 0)
         tex = sum(v[0] for v in by.values())
         tsm = sum(v[1] for v in by.values())
-        print("\n  executed warp instructions by opcode (source counters of the same capture)")
+        print("\n  executed warp instructions by opcode (source counters of the same capture, all profiled launches)")
         print("  opcode      %instructions  %stall-samples  smem wavefronts/instruction")
         for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])[:14]:
             print(f"  {k:10s} {100 * v[0] / tex:12.1f} {100 * v[1] / max(1, tsm):15.1f} {v[2] / max(1, v[0]):12.2f}")
