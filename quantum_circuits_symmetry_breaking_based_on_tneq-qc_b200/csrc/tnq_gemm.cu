@@ -38,6 +38,7 @@
 // drain before the next MMA into that accumulator, so no extra synchronisation is needed; the
 // 2^-11 smaller correction terms (hi*lo + lo*hi) keep one accumulator for the whole k-loop
 // (their truncation error is 2^-11 smaller too).
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -366,6 +367,259 @@ tnq_gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B,
     }
 }
 
+
+// =====================================================================================================
+// TMA-fed variant (the default whenever the operands qualify: 16-byte aligned base / leading dimension / batch
+// stride).  Same arithmetic, accumulators, drain and epilogue as above; what changes is how the operands
+// reach shared memory:
+//   * ONE thread issues cp.async.bulk.tensor (SASS UTMALDG) per operand and k-block: the raw fp32 tile
+//     (128 rows x 32 floats = 128-byte rows) lands in the 128-byte-swizzled K-major layout the tensor core
+//     reads; out-of-range rows / columns (tile tails in M, N and K) arrive as zeros from the TMA unit;
+//   * the tensor core reads the RAW tile as the TF32 "hi" operand: kind::tf32 ignores the 13 low mantissa
+//     bits of a 32-bit operand, i.e. hi = trunc(v) without any instruction spent on it;
+//   * the eight worker warps only produce lo = rna_tf32(v - trunc(v)): v - trunc(v) is exact in fp32, the
+//     conversion is element-wise and therefore layout agnostic (read 16 bytes at an offset of the raw tile,
+//     write 16 bytes at the same offset of the lo tile: the swizzle never has to be computed);
+//   * raw ring (NRAW stages, filled by TMA) and lo ring (NLO stages, one hi*hi accumulator each) are
+//     decoupled, so the loads run further ahead than the conversion.
+// Barriers: full_raw[NRAW] (TMA transaction bytes), full_lo[NLO] (256 worker arrivals; also: the stage's
+// accumulator has been drained), done[NRAW] (tcgen05.commit of a k-block: its raw stage, its lo stage and
+// its accumulator are free), accum (everything retired).
+// =====================================================================================================
+constexpr int RAW_BYTES = 2 * TILE_BYTES;            // A | B of one k-block
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// UMMA shared-memory descriptor, K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
+// (SBO); LBO is not used by swizzled K-major layouts; a K=8 step advances the start address by 32 bytes inside
+// the swizzle atom (the hardware applies the XOR to the absolute address bits: tiles are 1024-byte aligned).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void issue_kblock_tma(uint32_t raw, uint32_t lo, uint32_t tmem_h, uint32_t tmem_corr, int kb, bool last,
+                                                 uint32_t done_bar, uint32_t accum_bar) {
+#pragma unroll
+    for (int j = 0; j < BK / 8; ++j) {
+        const uint32_t ko = (uint32_t)j * 32u;
+        const uint64_t a_hi = umma_desc_sw128(raw + ko), a_lo = umma_desc_sw128(lo + ko);
+        const uint64_t b_hi = umma_desc_sw128(raw + TILE_BYTES + ko), b_lo = umma_desc_sw128(lo + TILE_BYTES + ko);
+        umma_tf32(tmem_corr, a_lo, b_hi, (kb | j) != 0);
+        umma_tf32(tmem_corr, a_hi, b_lo, 1u);
+        umma_tf32(tmem_h, a_hi, b_hi, j != 0);
+    }
+    umma_commit(done_bar);
+    if (last) umma_commit(accum_bar);
+}
+
+// SOLO: no dedicated TMA / MMA warps (256 threads, lane 0 of warp 0 issues both; NLO = 1) -- the small-K regime,
+// two CTAs per SM so that one tile's epilogue overlaps the other's main loop.
+template <int NRAW, int NLO, bool SOLO>
+__global__ void __maxnreg__(SOLO ? 128 : 168)
+tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+                    long long M, long long N, long long K, long long ldc, long long strideC, int zA, int zB, int accumulate,
+                    int rewrite_hi) {
+    static_assert(!SOLO || NLO == 1, "the solo variant serialises conversion and MMA");
+    static_assert(NRAW >= NLO, "done[] is indexed by the raw stage");
+    constexpr uint32_t NCOLS = (NLO + 1) * BN <= 256 ? 256u : 512u;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bars[2 * NRAW + NLO + 1];
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * BN;
+    C += (long long)blockIdx.z * strideC;
+    const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+    const uint32_t raw0 = smem_base, lo0 = smem_base + (uint32_t)NRAW * RAW_BYTES;
+    const uint32_t full_raw0 = smem_u32(&bars[0]), done0 = smem_u32(&bars[NRAW]), full_lo0 = smem_u32(&bars[2 * NRAW]),
+                   accum_bar = smem_u32(&bars[2 * NRAW + NLO]);
+    if (tid == 0) {
+        for (int s = 0; s < NRAW; ++s) {
+            mbar_init(full_raw0 + 8 * s, 1);
+            mbar_init(done0 + 8 * s, 1);
+        }
+        for (int s = 0; s < NLO; ++s) mbar_init(full_lo0 + 8 * s, PRODUCERS);
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    }
+    constexpr int ALLOC_WARP = SOLO ? 1 : PRODUCERS / 32;
+    if (warp == ALLOC_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(NCOLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t tmem_corr = tmem_base + (uint32_t)(NLO * BN);
+    const int nkb = (int)((K + BK - 1) / BK);
+    const int za = zA ? (int)blockIdx.z : 0, zb = zB ? (int)blockIdx.z : 0;
+
+    auto load_kblock = [&](int kb) {                     // one thread
+        const int sr = kb % NRAW;
+        const uint32_t dst = raw0 + (uint32_t)sr * RAW_BYTES, bar = full_raw0 + 8 * sr;
+        mbar_expect_tx(bar, RAW_BYTES);
+        tma_load_3d(dst, &tmA, bar, kb * BK, (int)m0, za);
+        tma_load_3d(dst + TILE_BYTES, &tmB, bar, kb * BK, (int)n0, zb);
+    };
+
+    if (warp < PRODUCERS / 32) {
+        // ---------------- workers: drain, lo conversion, epilogue ----------------
+        const int quad = warp & 3, chalf = warp >> 2;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * 64);
+        float sum[64];
+        bool have = false;
+        if (SOLO && tid == 0)
+            for (int kb = 0; kb < NRAW && kb < nkb; ++kb) load_kblock(kb);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int sr = kb % NRAW, sl = kb % NLO;
+            if (kb >= NLO) {      // k-block kb - NLO has retired: its lo stage is free and its accumulator complete
+                const int j = kb - NLO;
+                mbar_wait(done0 + 8 * (j % NRAW), (uint32_t)(j / NRAW) & 1u);
+                if (SOLO && tid == 0 && j + NRAW < nkb) load_kblock(j + NRAW);   // (NLO == 1: j = kb - 1, its raw stage is free too)
+                if (SOLO) __syncwarp();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                drain_add(tlane + (uint32_t)(sl * BN), sum, !have);
+                have = true;
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+            mbar_wait(full_raw0 + 8 * sr, (uint32_t)(kb / NRAW) & 1u);      // the raw tiles have landed
+            const uint32_t raw = raw0 + (uint32_t)sr * RAW_BYTES, lo = lo0 + (uint32_t)sl * RAW_BYTES;
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t off = (uint32_t)(i * PRODUCERS + tid) * 16u;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(raw + off));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t off = (uint32_t)(i * PRODUCERS + tid) * 16u;
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u), h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
+                h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u), h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
+                // lo rounded to nearest TF32: the tensor core would truncate it (a biased error)
+                l.x = tf32_hi(v[i].x - h.x), l.y = tf32_hi(v[i].y - h.y), l.z = tf32_hi(v[i].z - h.z), l.w = tf32_hi(v[i].w - h.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                if (rewrite_hi)   // diagnostics: do not rely on the tensor core ignoring the low mantissa bits
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(raw + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(full_lo0 + 8 * sl);
+            if (SOLO && warp == 0) {
+                mbar_wait(full_lo0 + 8 * sl, (uint32_t)(kb / NLO) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0)
+                    issue_kblock_tma(raw, lo, tmem_base + (uint32_t)(sl * BN), tmem_corr, kb, kb == nkb - 1, done0 + 8 * sr, accum_bar);
+                __syncwarp();
+            }
+        }
+        // ---------------- epilogue ----------------
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int pending = nkb < NLO ? nkb : NLO;
+#pragma unroll 1
+        for (int i = 0; i < pending; ++i) {
+            drain_add(tlane + (uint32_t)(((nkb - pending + i) % NLO) * BN), sum, !have);
+            have = true;
+        }
+        drain_add(tmem_corr - tmem_base + tlane, sum, false);
+        float* xpose = reinterpret_cast<float*>(smem + (smem_base - smem_u32(smem))) + warp * (32 * 33);   // the rings are idle now
+        store_tile(sum, xpose, lane, C, ldc, m0 + quad * 32, n0 + chalf * 64, M, N, accumulate);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else if (!SOLO && warp == PRODUCERS / 32) {
+        // ---------------- MMA issuer ----------------
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int sr = kb % NRAW, sl = kb % NLO;
+            mbar_wait(full_lo0 + 8 * sl, (uint32_t)(kb / NLO) & 1u);
+            mbar_wait(full_raw0 + 8 * sr, (uint32_t)(kb / NRAW) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0)
+                issue_kblock_tma(raw0 + (uint32_t)sr * RAW_BYTES, lo0 + (uint32_t)sl * RAW_BYTES, tmem_base + (uint32_t)(sl * BN), tmem_corr,
+                                 kb, kb == nkb - 1, done0 + 8 * sr, accum_bar);
+            __syncwarp();
+        }
+    } else if (!SOLO) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                if (kb >= NRAW) mbar_wait(done0 + 8 * (kb % NRAW), (uint32_t)((kb - NRAW) / NRAW) & 1u);
+                load_kblock(kb);
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == ALLOC_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NCOLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// (k, row, batch) view of a row-major operand with 128 x 32 boxes in the 128-byte swizzle.  false: not expressible
+// (alignment, extents) -- the caller takes the register-staged kernel.
+bool make_operand_map(CUtensorMap* map, const float* base, long long rows, long long K, long long ld, long long batch,
+                      long long stride, int* uses_z) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    if (((uintptr_t)base & 15) || (ld & 3) || ld < K || K > 0x7fffffffLL || rows > 0x7fffffffLL) return false;
+    const bool z = batch > 1 && stride != 0;
+    if (z && ((stride & 3) || stride < rows * ld || batch > 0x7fffffffLL)) return false;
+    *uses_z = z ? 1 : 0;
+    long long s2 = z ? stride : rows * ld;
+    s2 = (s2 + 3) & ~3LL;
+    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(z ? batch : 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)s2 * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NRAW, int NLO, bool SOLO>
+int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long M, long long N, long long K, long long ldc,
+               long long strideC, long long batch, int zA, int zB, int accumulate, int rewrite_hi, cudaStream_t st) {
+    const size_t smem = (size_t)(NRAW + NLO) * RAW_BYTES + 1024;
+    auto kern = tnq_gemm_tma_kernel<NRAW, NLO, SOLO>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(gemm tma)");
+    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
+    kern<<<grid, SOLO ? PRODUCERS : PRODUCERS + 64, smem, st>>>(ta, tb, C, M, N, K, ldc, strideC, zA, zB, accumulate, rewrite_hi);
+    tnq_internal_count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_gemm_tf32x3 (TMA) launch");
+    return 0;
+}
+
 }  // namespace
 
 // launch resources of one kernel variant (tests / diagnostics): out = {registers per thread, max threads per block,
@@ -389,6 +643,22 @@ extern "C" int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t
                            ((uintptr_t)B & 15));
     if (batch > 65535) return tnq_internal_fail("tnq_gemm_tf32x3: batch too large for one launch (max 65535)");
     const bool smallk = K <= 256 && !getenv("TNQ_GEMM_NO_SMALLK");
+    // TMA-fed kernels whenever both operands can be described by a tensor map (TNQ_GEMM_NO_TMA=1: the
+    // register-staged kernels below; TNQ_GEMM_TMA_STAGES=42: raw ring of 4 + lo ring of 2 instead of 3 + 3)
+    static const bool no_tma = getenv("TNQ_GEMM_NO_TMA") != nullptr;
+    if (!no_tma) {
+        CUtensorMap ta, tb;
+        int zA = 0, zB = 0;
+        if (make_operand_map(&ta, A, M, K, lda, batch, strideA, &zA) && make_operand_map(&tb, B, N, K, ldb, batch, strideB, &zB)) {
+            static const int rewrite_hi = getenv("TNQ_GEMM_TMA_REWRITE_HI") ? 1 : 0;
+            static const int stages = getenv("TNQ_GEMM_TMA_STAGES") ? atoi(getenv("TNQ_GEMM_TMA_STAGES")) : 33;
+            if (smallk)
+                return launch_tma<2, 1, true>(ta, tb, C, M, N, K, ldc, strideC, batch, zA, zB, accumulate, rewrite_hi, (cudaStream_t)stream);
+            if (stages == 42)
+                return launch_tma<4, 2, false>(ta, tb, C, M, N, K, ldc, strideC, batch, zA, zB, accumulate, rewrite_hi, (cudaStream_t)stream);
+            return launch_tma<3, 3, false>(ta, tb, C, M, N, K, ldc, strideC, batch, zA, zB, accumulate, rewrite_hi, (cudaStream_t)stream);
+        }
+    }
     const size_t smem = (size_t)(smallk ? 1 : STAGES) * STAGE_BYTES + 1024;
     auto kern = smallk ? (aligned ? tnq_gemm_tf32x3_kernel<true, true> : tnq_gemm_tf32x3_kernel<false, true>)
                        : (aligned ? tnq_gemm_tf32x3_kernel<true, false> : tnq_gemm_tf32x3_kernel<false, false>);

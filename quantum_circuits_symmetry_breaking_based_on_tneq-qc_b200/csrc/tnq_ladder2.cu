@@ -151,9 +151,11 @@ int ctas_per_sm(int R, int NW, int mode, int smem_sm) {
     return c < 1 ? 1 : c;
 }
 
-// Geometry: tiles of 32 / R samples, NW warps per CTA.  Large batches: 4-warp CTAs, two per SM (training), the tile
-// size that keeps the tail short.  Batches that leave SMs idle at one 4-warp CTA per tile: 8-warp CTAs (R = 2 or 4),
-// half the row blocks per warp, i.e. about half the latency of a tile -- the per-GPU batch of the 8-GPU run.
+// Geometry: tiles of 32 / R samples, NW warps per CTA: 4-warp CTAs, two per SM (training), the tile size that keeps the
+// tail short.  8-warp CTAs (R = 2 or 4, half the row blocks per warp) exist for experiments (TNQ_LADDER_WARPS=8): measured
+// on B200 at 2 048 / 4 096 samples they are SLOWER than 4-warp CTAs (0.33-0.47 ms vs 0.25 ms; 0.63 vs 0.41 ms of the
+// first-generation kernel): the CTA barriers between the small phases cost more with twice the warps than the shorter
+// row-block loop saves.
 Plan make_plan(int n, long long B, int mode, int sms, int smem_sm) {
     (void)n;
     Plan best{};
@@ -164,7 +166,7 @@ Plan make_plan(int n, long long B, int mode, int sms, int smem_sm) {
         for (int R = 1; R <= 8; R *= 2) {
             if (NW == 8 && R != 2 && R != 4) continue;
             if (force && atoi(force) != R) continue;
-            if (force_w && atoi(force_w) != NW) continue;
+            if (force_w ? atoi(force_w) != NW : NW != 4) continue;     // 8-warp CTAs only on request (measured slower)
             if (smem_of(R, NW, mode) + 1024 > (size_t)smem_sm) continue;
             const int S = 32 / R;
             const long long ntiles = (B + S - 1) / S;
