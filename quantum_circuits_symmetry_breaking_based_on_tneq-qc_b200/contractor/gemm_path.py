@@ -71,6 +71,12 @@ class GemmPathRunner:
         given order, `rows` in any order (their current order is kept when no copy is needed)
         unless exact.  Returns (tensor, order of the row indices).  At most one permute kernel."""
         k = len(cols)
+        if not exact:
+            # rows in the order they have in memory: indices that are neighbours in the input stay neighbours in
+            # the output, so tnq_permute_f32 can merge them into one contiguous run (a (index, re/im) pair split
+            # by another row index forced the strided scalar path: 2.1 ms instead of 0.5 ms per 537 MB tensor)
+            rs = set(rows)
+            rows = [i for i in layout if i in rs]
         head, tail = layout[: len(layout) - k], layout[len(layout) - k:]
         if tail == list(cols) and (head == list(rows) if exact else sorted(head) == sorted(rows)):
             return t, head

@@ -208,7 +208,8 @@ __device__ __forceinline__ void store_tile(const float (&sum)[64], float* xpose,
             if (row < M && col < N) {
                 float* d = C + row * ldc + col;
                 const float v = xpose[rr * 33 + lane];
-                *d = accumulate ? *d + v : v;
+                if (accumulate == 2) atomicAdd(d, v);        // split-K: two CTAs add into a zeroed tile (two addends commute: deterministic)
+                else *d = accumulate ? *d + v : v;
             }
         }
         __syncwarp();
@@ -430,7 +431,7 @@ template <int NRAW, int NLO, bool SOLO>
 __global__ void __maxnreg__(SOLO ? 128 : 168)
 tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
                     long long M, long long N, long long K, long long ldc, long long strideC, int zA, int zB, int accumulate,
-                    int rewrite_hi) {
+                    int rewrite_hi, int splitk) {
     static_assert(!SOLO || NLO == 1, "the solo variant serialises conversion and MMA");
     static_assert(NRAW >= NLO, "done[] is indexed by the raw stage");
     constexpr uint32_t NCOLS = (NLO + 1) * BN <= 256 ? 256u : 512u;
@@ -439,7 +440,7 @@ tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * BN;
-    C += (long long)blockIdx.z * strideC;
+    if (splitk <= 1) C += (long long)blockIdx.z * strideC;
     const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
     const uint32_t raw0 = smem_base, lo0 = smem_base + (uint32_t)NRAW * RAW_BYTES;
     const uint32_t full_raw0 = smem_u32(&bars[0]), done0 = smem_u32(&bars[NRAW]), full_lo0 = smem_u32(&bars[2 * NRAW]),
@@ -467,15 +468,19 @@ tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
     const uint32_t tmem_corr = tmem_base + (uint32_t)(NLO * BN);
-    const int nkb = (int)((K + BK - 1) / BK);
-    const int za = zA ? (int)blockIdx.z : 0, zb = zB ? (int)blockIdx.z : 0;
+    // split-K (splitk > 1, batch == 1): blockIdx.z owns the k-blocks [kb0, kb0 + nkb) and adds its partial tile atomically
+    const int nkb_all = (int)((K + BK - 1) / BK);
+    const int kb0 = splitk > 1 ? (int)((long long)nkb_all * blockIdx.z / splitk) : 0;
+    const int nkb = splitk > 1 ? (int)((long long)nkb_all * (blockIdx.z + 1) / splitk) - kb0 : nkb_all;
+    const int za = (zA && splitk <= 1) ? (int)blockIdx.z : 0, zb = (zB && splitk <= 1) ? (int)blockIdx.z : 0;
+    if (splitk > 1) accumulate = 2;
 
     auto load_kblock = [&](int kb) {                     // one thread
         const int sr = kb % NRAW;
         const uint32_t dst = raw0 + (uint32_t)sr * RAW_BYTES, bar = full_raw0 + 8 * sr;
         mbar_expect_tx(bar, RAW_BYTES);
-        tma_load_3d(dst, &tmA, bar, kb * BK, (int)m0, za);
-        tma_load_3d(dst + TILE_BYTES, &tmB, bar, kb * BK, (int)n0, zb);
+        tma_load_3d(dst, &tmA, bar, (kb0 + kb) * BK, (int)m0, za);
+        tma_load_3d(dst + TILE_BYTES, &tmB, bar, (kb0 + kb) * BK, (int)n0, zb);
     };
 
     if (warp < PRODUCERS / 32) {
@@ -608,12 +613,24 @@ bool make_operand_map(CUtensorMap* map, const float* base, long long rows, long 
 template <int NRAW, int NLO, bool SOLO>
 int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long M, long long N, long long K, long long ldc,
                long long strideC, long long batch, int zA, int zB, int accumulate, int rewrite_hi, cudaStream_t st) {
+    // split-K by two when a long k-loop would leave more than half of the SMs without a tile (the core-gradient GEMMs
+    // of the bond-64 sweep: 64 tiles, K = 16 384): C is zeroed, both halves add atomically
+    int splitk = 1;
+    if (!SOLO && batch == 1 && !accumulate && ((N + BN - 1) / BN) * ((M + BM - 1) / BM) <= 74 && K >= 32 * BK) {
+        static const bool no_split = getenv("TNQ_GEMM_NO_SPLITK") != nullptr;
+        if (!no_split) splitk = 2;
+    }
+    if (splitk > 1) {
+        cudaError_t e0 = ldc == N ? cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * (size_t)N, st)
+                                  : cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, st);
+        if (e0 != cudaSuccess) return tnq_internal_cuda_fail(e0, "cudaMemsetAsync(gemm split-K)");
+    }
     const size_t smem = (size_t)(NRAW + NLO) * RAW_BYTES + 1024;
     auto kern = tnq_gemm_tma_kernel<NRAW, NLO, SOLO>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(gemm tma)");
-    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
-    kern<<<grid, SOLO ? PRODUCERS : PRODUCERS + 64, smem, st>>>(ta, tb, C, M, N, K, ldc, strideC, zA, zB, accumulate, rewrite_hi);
+    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)(splitk > 1 ? splitk : batch));
+    kern<<<grid, SOLO ? PRODUCERS : PRODUCERS + 64, smem, st>>>(ta, tb, C, M, N, K, ldc, strideC, zA, zB, accumulate, rewrite_hi, splitk);
     tnq_internal_count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_gemm_tf32x3 (TMA) launch");
@@ -644,14 +661,14 @@ extern "C" int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t
     if (batch > 65535) return tnq_internal_fail("tnq_gemm_tf32x3: batch too large for one launch (max 65535)");
     const bool smallk = K <= 256 && !getenv("TNQ_GEMM_NO_SMALLK");
     // TMA-fed kernels whenever both operands can be described by a tensor map (TNQ_GEMM_NO_TMA=1: the
-    // register-staged kernels below; TNQ_GEMM_TMA_STAGES=42: raw ring of 4 + lo ring of 2 instead of 3 + 3)
+    // register-staged kernels below; TNQ_GEMM_TMA_STAGES=33: raw ring of 3 + lo ring of 3 instead of 4 + 2, measured 6 % slower at K = 8192)
     static const bool no_tma = getenv("TNQ_GEMM_NO_TMA") != nullptr;
     if (!no_tma) {
         CUtensorMap ta, tb;
         int zA = 0, zB = 0;
         if (make_operand_map(&ta, A, M, K, lda, batch, strideA, &zA) && make_operand_map(&tb, B, N, K, ldb, batch, strideB, &zB)) {
             static const int rewrite_hi = getenv("TNQ_GEMM_TMA_REWRITE_HI") ? 1 : 0;
-            static const int stages = getenv("TNQ_GEMM_TMA_STAGES") ? atoi(getenv("TNQ_GEMM_TMA_STAGES")) : 33;
+            static const int stages = getenv("TNQ_GEMM_TMA_STAGES") ? atoi(getenv("TNQ_GEMM_TMA_STAGES")) : 42;
             if (smallk)
                 return launch_tma<2, 1, true>(ta, tb, C, M, N, K, ldc, strideC, batch, zA, zB, accumulate, rewrite_hi, (cudaStream_t)stream);
             if (stages == 42)

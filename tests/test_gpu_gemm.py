@@ -32,7 +32,9 @@ def _gemm(A, B, C=None, accumulate=False):
 
 
 @pytest.mark.parametrize("M,N,K,nb", [(128, 128, 32, 1), (128, 128, 128, 1), (256, 384, 96, 1), (100, 72, 36, 1),
-                                      (1, 8, 4, 1), (300, 130, 260, 3), (4096, 128, 128, 2), (64, 8192, 128, 1)])
+                                      (1, 8, 4, 1), (300, 130, 260, 3), (4096, 128, 128, 2), (64, 8192, 128, 1),
+                                      # long k-loop over few tiles: split-K by two (atomic adds into a zeroed tile)
+                                      (128, 384, 4096, 1), (100, 130, 1500, 1)])
 def test_gemm_matches_float64(M, N, K, nb, built_lib):
     torch.manual_seed(M * 7 + N * 3 + K)
     A = torch.randn(nb, M, K, device="cuda")

@@ -189,7 +189,11 @@ def test_permute_kernel_paths(built_lib):
     lib = _lib.load()
     torch.manual_seed(0)
     cases = [((6, 40, 50), (2, 1, 0), 1), ((3, 33, 65, 2), (2, 0, 1, 3), 2), ((64, 64, 64), (1, 2, 0), 1),
-             ((5, 7, 9, 4), (0, 2, 1, 3), 4), ((130, 70), (1, 0), 1), ((8, 3, 3, 2), (0, 2, 1, 3), 2)]
+             ((5, 7, 9, 4), (0, 2, 1, 3), 4), ((130, 70), (1, 0), 1), ((8, 3, 3, 2), (0, 2, 1, 3), 2),
+             # neighbours that merge into one input-contiguous run (the batch-into-K transposition of the bond-64
+             # gradient GEMMs), vector widening (vec 2 -> 4), extent-1 dimensions, plain copies
+             ((5, 6, 12, 16, 2), (1, 3, 4, 0, 2), 1), ((3, 5, 7, 8, 2), (0, 2, 1, 3, 4), 2), ((3, 5, 7, 6, 2), (0, 2, 1, 3, 4), 2),
+             ((1, 5, 1, 4), (2, 0, 1, 3), 1), ((4,), (0,), 1), ((7, 9, 8), (0, 1, 2), 1), ((2, 40, 3, 36, 2), (2, 3, 4, 0, 1), 1)]
     for shape, perm, vec in cases:
         x = torch.randn(*shape, device="cuda")
         want = x.permute(*perm).contiguous()
