@@ -129,6 +129,59 @@ __global__ void __launch_bounds__(256) permute_tiled_kernel(const float* __restr
     }
 }
 
+// tiled path for scalar elements with 16-byte accesses on BOTH sides: a 64 x 64 float tile, float4 global loads along
+// a (contiguous in the input), float4 global stores along b (contiguous in the output), transposed through a
+// [64][65] shared tile with scalar accesses (two-way bank conflicts at most).  Used when extents, strides and
+// pointers are multiples of four floats -- the batch-into-K transpositions of the bond-64 gradient GEMMs.
+__global__ void __launch_bounds__(256) permute_tiled64_kernel(const float* __restrict__ in, float* __restrict__ out, Dims d,
+                                                              int da, long long ostride_a, long long tiles_a, long long tiles_b,
+                                                              long long ntiles) {
+    __shared__ float tile[64][65];
+    const int x = threadIdx.x & 15, y = threadIdx.x >> 4;     // 16 float4 columns x 16 rows
+    const int db = d.nd - 1;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        long long rem = t;
+        const long long tb = rem % tiles_b;
+        rem /= tiles_b;
+        const long long ta = rem % tiles_a;
+        rem /= tiles_a;
+        long long ioff = 0, ooff = 0, ostr = 1;
+        long long ostride[MAXD];
+        for (int k = d.nd - 1; k >= 0; --k) {
+            ostride[k] = ostr;
+            ostr *= d.size[k];
+        }
+        for (int k = d.nd - 2; k >= 0; --k) {
+            if (k == da) continue;
+            const long long q = rem / d.size[k];
+            const long long idx = rem - q * d.size[k];
+            ioff += idx * d.istride[k];
+            ooff += idx * ostride[k];
+            rem = q;
+        }
+        const long long a0 = ta * 64, b0 = tb * 64;
+#pragma unroll
+        for (int j = y; j < 64; j += 16) {          // rows along b, float4 along a
+            const long long a = a0 + 4 * x, b = b0 + j;
+            if (a < d.size[da] && b < d.size[db]) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(in + ioff + a + b * d.istride[db]));
+                tile[j][4 * x] = v.x, tile[j][4 * x + 1] = v.y, tile[j][4 * x + 2] = v.z, tile[j][4 * x + 3] = v.w;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = y; j < 64; j += 16) {          // rows along a, float4 along b
+            const long long a = a0 + j, b = b0 + 4 * x;
+            if (a < d.size[da] && b < d.size[db]) {
+                float4 v;
+                v.x = tile[4 * x][j], v.y = tile[4 * x + 1][j], v.z = tile[4 * x + 2][j], v.w = tile[4 * x + 3][j];
+                *reinterpret_cast<float4*>(out + ooff + a * ostride_a + b) = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Qx[o] = sign * Q[i(o)] with the two extra output dimensions ri (dim pa) and ro (dim pb):
 // c = ri ^ ro, sign = -1 for (ri, ro) = (1, 0); conj flips the sign of c = 1.
 __global__ void __launch_bounds__(256) cplx_expand_kernel(const float* __restrict__ in, float* __restrict__ out, Dims d,
@@ -279,6 +332,28 @@ int tnq_permute_f32(const float* in, float* out, int ndim, const int64_t* out_di
     } else {
         long long ostride_a = 1;
         for (int k = d.nd - 1; k > da; --k) ostride_a *= d.size[k];
+        bool wide = vec == 1 && !conj && d.size[da] % 4 == 0 && d.size[d.nd - 1] % 4 == 0 && ostride_a % 4 == 0 &&
+                    d.size[da] >= 32 && d.size[d.nd - 1] >= 32 && !(((uintptr_t)in | (uintptr_t)out) & 15);
+        for (int k = 0; k < d.nd && wide; ++k)
+            if (k != da) wide = d.istride[k] % 4 == 0;
+        if (wide) {
+            long long os = 1;                        // every output stride above the last dimension is a multiple of four
+            for (int k = d.nd - 1; k >= 1 && wide; --k) {
+                os *= d.size[k];
+                wide = os % 4 == 0;
+            }
+        }
+        if (wide) {
+            const long long tiles_a = (d.size[da] + 63) / 64, tiles_b = (d.size[d.nd - 1] + 63) / 64;
+            long long ntiles = tiles_a * tiles_b;
+            for (int k = 0; k < d.nd - 1; ++k)
+                if (k != da) ntiles *= d.size[k];
+            permute_tiled64_kernel<<<grid_for(ntiles, 1), 256, 0, st>>>(in, out, d, da, ostride_a, tiles_a, tiles_b, ntiles);
+            tnq_internal_count_launch();
+            cudaError_t e64 = cudaGetLastError();
+            if (e64 != cudaSuccess) return tnq_internal_cuda_fail(e64, "tnq_permute_f32 launch");
+            return 0;
+        }
         const long long tiles_a = (d.size[da] + 31) / 32, tiles_b = (d.size[d.nd - 1] + 31) / 32;
         long long ntiles = tiles_a * tiles_b;
         for (int k = 0; k < d.nd - 1; ++k)

@@ -193,7 +193,9 @@ def test_permute_kernel_paths(built_lib):
              # neighbours that merge into one input-contiguous run (the batch-into-K transposition of the bond-64
              # gradient GEMMs), vector widening (vec 2 -> 4), extent-1 dimensions, plain copies
              ((5, 6, 12, 16, 2), (1, 3, 4, 0, 2), 1), ((3, 5, 7, 8, 2), (0, 2, 1, 3, 4), 2), ((3, 5, 7, 6, 2), (0, 2, 1, 3, 4), 2),
-             ((1, 5, 1, 4), (2, 0, 1, 3), 1), ((4,), (0,), 1), ((7, 9, 8), (0, 1, 2), 1), ((2, 40, 3, 36, 2), (2, 3, 4, 0, 1), 1)]
+             ((1, 5, 1, 4), (2, 0, 1, 3), 1), ((4,), (0,), 1), ((7, 9, 8), (0, 1, 2), 1), ((2, 40, 3, 36, 2), (2, 3, 4, 0, 1), 1),
+             # the 64 x 64 float4 tile path (extents and strides multiples of four), with ragged tile edges
+             ((3, 100, 5, 72), (2, 3, 0, 1), 1), ((4, 64, 2, 68, 2), (1, 3, 4, 0, 2), 1), ((132, 260), (1, 0), 1)]
     for shape, perm, vec in cases:
         x = torch.randn(*shape, device="cuda")
         want = x.permute(*perm).contiguous()
