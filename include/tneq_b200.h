@@ -109,6 +109,19 @@ int tnq_mps_chain_x(int K, int n, const float* const* cores, const float* const*
                     int64_t xs_q, const float* weights, int64_t B, float* scale, float* values, void* stream);
 
 /*
+ * sample() with prefix environments for single-layer MPS networks (replaces the n full forwards at batch
+ * num_samples x grid_size of EngineSiamese.sample, tneq_qc/core/engine_siamese.py:740-915: grid expansion :802-822,
+ * forward :842-847, inverse CDF :855-905).  One thread per sample walks the chain once: left environment in
+ * registers, right environments (identity measurements) shared, the value linear in the measurement matrix of the
+ * qubit being sampled, cumulative sum / search / interpolation / generate_data of the sampled value on the device.
+ *   grid_x[G]; mx_grid[G][K][K] = generate_data(grid_x); u[S][n] uniform numbers in the reference's draw order
+ *   (one (S,1) draw per qubit; qubit q of sample s at u[s*n + q]); weights[K] (host) -> samples[S][n].
+ */
+int tnq_mps_chain_sample(int K, int n, const float* const* cores, const float* const* states, int64_t S, int G,
+                         const float* grid_x, const float* mx_grid, const float* u, const float* weights, float* samples,
+                         void* stream);
+
+/*
  * Warp-level sweep for TWO-LAYER merged MPS networks (QCTN.merge(mps_n, mps_n), reference
  * tneq_qc/core/qctn.py:1296-1506; BASELINE cfg3), float32, edge rank K in {2,3}, n >= 3: the greedy
  * sweep greedy_strategy.py:461-598 with its rank-6 environment kept in shared memory by the warp that

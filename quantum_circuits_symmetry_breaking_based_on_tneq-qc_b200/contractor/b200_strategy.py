@@ -785,6 +785,53 @@ class B200Strategy(ContractionStrategy):
                                                    c_void_p(torch.cuda.current_stream(device).cuda_stream)))
             return values, scale
 
+        def sample_prefix(cores_dict, circuit_states, grid_x, mx_grid, u, weights):
+            """sample() with prefix environments (tnq_mps_chain_sample): grid_x (G,), mx_grid (G,K,K) =
+            generate_data(grid_x), u (S, n) uniform numbers in the reference's draw order, weights: the K Hermite
+            weights.  Returns samples (S, n), or None when this network / these operands are not on the single-layer
+            MPS route (the caller then takes the contraction-based procedure)."""
+            from ctypes import c_void_p, c_float
+            K = len(weights)
+            if right_mode == "qctn" or u.dim() != 2 or u.shape[1] != nq or u.dtype != torch.float32 or not u.is_cuda:
+                return None
+            if mx_grid.dtype != torch.float32 or tuple(mx_grid.shape[1:]) != (K, K) or grid_x.dtype != torch.float32:
+                return None
+            states_w = _items(circuit_states, nq)
+            cores = [cores_dict[k] for k in core_names]
+            cores = [c.tensor * c.scale if _is_tnt(c) else c for c in cores]
+            states = {q: (v.tensor * v.scale if _is_tnt(v) else v) for q, v in states_w.items()}
+            device = u.device
+            if len(states) != nq or any(t.dtype != torch.float32 or t.device != device for t in cores) or \
+                    any(t.dtype != torch.float32 or t.device != device or t.dim() != 1 for t in states.values()):
+                return None
+            key = (tuple((q, t.shape[0]) for q, t in states.items()), tuple((q, 3, K, K) for q in range(nq)),
+                   torch.float32, device)
+            bound = plans.get(key)
+            if bound is None:
+                state_dims = {q: int(t.shape[0]) for q, t in states.items()}
+                mx_info = {q: ("a", K, K) for q in range(nq)}
+                shapes = {k: tuple(t.shape) for k, t in zip(core_names, cores)}
+                plan = ContractionPlan(table, nq, shapes, state_dims, mx_info, "float32", right=right_mode)
+                bound = plans[key] = _Bound(plan, device)
+            if bound.chain_rank != K:
+                return None
+            lib = _lib_mod.load()
+            order = [k[1] for k in bound.plan.core_shapes]
+            by_name = dict(zip(core_names, cores))
+            cs = [by_name[k].detach().contiguous() for k in order]
+            sts = [states[q].detach().contiguous() for q in range(nq)]
+            S, G = int(u.shape[0]), int(grid_x.shape[0])
+            gx, mg, uu = grid_x.to(device).contiguous(), mx_grid.to(device).contiguous(), u.contiguous()
+            samples = torch.empty(S, nq, dtype=torch.float32, device=device)
+            arr = lambda ts: (c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+            with torch.cuda.device(device):
+                _lib_mod.check(lib.tnq_mps_chain_sample(K, nq, arr(cs), arr(sts), S, G, c_void_p(gx.data_ptr()),
+                                                        c_void_p(mg.data_ptr()), c_void_p(uu.data_ptr()),
+                                                        (c_float * K)(*[float(w) for w in weights]),
+                                                        c_void_p(samples.data_ptr()),
+                                                        c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+            return samples
+
         def equations(circuit_states, measure_matrices):
             """The per-qubit einsum strings of this signature (index bookkeeping parity)."""
             sd, mi = signature_of(nq, circuit_states, measure_matrices)
@@ -797,5 +844,6 @@ class B200Strategy(ContractionStrategy):
         compute_fn.graph_stats = graphs
         compute_fn.equations = equations
         compute_fn.forward_from_x = forward_from_x
+        compute_fn.sample_prefix = sample_prefix
         compute_fn.plans = plans
         return compute_fn

@@ -313,8 +313,17 @@ class EngineSiamese:
         return res[:, 0] / (res[:, 1] + 1e-10)
 
     # ---- sampling (engine_siamese.py:740-915) --------------------------------------------
-    def sample(self, qctn, circuit_states_list, num_samples, K, bounds=[-5, 5], grid_size=1000, method="linear"):
+    def sample(self, qctn, circuit_states_list, num_samples, K, bounds=[-5, 5], grid_size=1000, method="auto"):
         """Qubit by qubit inverse-CDF sampling on a grid of `grid_size` points (engine_siamese.py:740-915).
+
+        method="prefix" (what "auto" picks for single-layer MPS networks in float32): the whole procedure in ONE
+        kernel launch (csrc/tnq_chain.cu: tnq_mps_chain_sample) -- a thread owns a sample, keeps the LEFT environment
+        of the qubits already sampled in registers and advances it by one chain step per qubit, the RIGHT
+        environments (identity measurements on the qubits still to come) are shared by all samples, a grid point
+        costs K^2 multiply-adds, and cumulative sum, search, interpolation and the sampled value's measurement
+        matrix stay on the device.  The reference redoes the prefix and suffix work for every grid point of every
+        qubit (n forwards at batch num_samples x grid_size).  Same densities up to float32 round-off, same random
+        draws (one (S,1) draw per qubit, in order); "auto" falls back to "linear" for every other network.
 
         method="grid" is the reference's procedure: one forward per qubit at batch num_samples x grid_size, every
         grid point a full contraction.  method="linear" (default) computes the SAME grid values from
@@ -326,12 +335,38 @@ class EngineSiamese:
         draws.  Everything after the densities (abs_square, clamp, cumsum, search, interpolation) is unchanged."""
         be = self.backend
         grid_x = be.linspace(bounds[0], bounds[1], steps=grid_size)
+        mx_grid = self.generate_data(be.unsqueeze(grid_x, 1), K=K)[0][0]          # (G,K,K)
+        if method not in ("auto", "prefix", "linear", "grid"):
+            raise ValueError("method must be 'auto', 'prefix', 'linear' or 'grid'")
+        if method in ("auto", "prefix"):
+            got = None
+            if not be.is_complex(mx_grid) and mx_grid.dtype == torch.float32 and mx_grid.is_cuda and grid_size >= 2:
+                probe = [torch.empty((num_samples, K, K), dtype=mx_grid.dtype, device="meta")] * qctn.nqubits
+                fn = self._compiled(qctn, list(circuit_states_list), probe, True, "symmetric")
+                if hasattr(fn, "sample_prefix"):
+                    # the reference's draws: one (S,1) uniform draw per qubit, in order (nothing else consumes the generator)
+                    u = torch.cat([be.rand((num_samples, 1), dtype=be.torch.float32) for _ in range(qctn.nqubits)], dim=1)
+                    cores = {name: qctn.cores_weights[name] for name in qctn.cores}
+                    got = fn.sample_prefix(cores, list(circuit_states_list), grid_x, mx_grid, u,
+                                           [float(w) for w in self._mx_weights_np[:K].astype(np.float32)])
+                    if got is None and method == "auto":
+                        # not a single-layer MPS: replay the SAME draws through the contraction-based procedure
+                        return self._sample_by_contraction(qctn, circuit_states_list, num_samples, K, grid_x, mx_grid,
+                                                           "linear", grid_size, draws=u)
+            if got is not None:
+                return got
+            if method == "prefix":
+                raise NotImplementedError("sample(method='prefix') needs a single-layer MPS network in float32 on the device")
+            method = "linear"
+        return self._sample_by_contraction(qctn, circuit_states_list, num_samples, K, grid_x, mx_grid, method, grid_size)
+
+    def _sample_by_contraction(self, qctn, circuit_states_list, num_samples, K, grid_x, mx_grid, method, grid_size,
+                               draws=None):
+        """methods "linear" and "grid" of sample(): one contraction per qubit (see there)."""
+        be = self.backend
         ident = be.expand(be.unsqueeze(be.eye(K), 0), num_samples, -1, -1)
         chosen = [ident for _ in range(qctn.nqubits)]
         samples = be.zeros((num_samples, qctn.nqubits))
-        mx_grid = self.generate_data(be.unsqueeze(grid_x, 1), K=K)[0][0]          # (G,K,K)
-        if method not in ("linear", "grid"):
-            raise ValueError("method must be 'linear' or 'grid'")
         if be.is_complex(mx_grid):
             method = "grid"        # complex backends report |amplitude|^2, which is not linear in the measurement
         units = be.reshape(be.eye(K * K), (K * K, K, K))                           # E_ab, (K^2,K,K)
@@ -353,7 +388,7 @@ class EngineSiamese:
             density = be.clamp(be.abs_square(res), min=0.0)
             cdf = be.cumsum(density, dim=1)
             cdf = cdf / (be.unsqueeze(cdf[:, -1], 1) + 1e-10)
-            u = be.rand((num_samples, 1), dtype=be.torch.float32)
+            u = be.rand((num_samples, 1), dtype=be.torch.float32) if draws is None else draws[:, q:q + 1]
             idx = be.clamp(be.sum((cdf < u).float(), dim=1).long(), max=grid_size - 2)
             idx = be.unsqueeze(idx, 1)
             c0, c1 = be.gather(cdf, 1, idx), be.gather(cdf, 1, idx + 1)

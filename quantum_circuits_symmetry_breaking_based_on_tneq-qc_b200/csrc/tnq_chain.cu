@@ -837,6 +837,151 @@ int launch_chain(const ChainArgs& a, long long B, int mode, const float* seed, f
     return 0;
 }
 
+
+// ---- sample(): qubit-by-qubit inverse-CDF sampling with PREFIX ENVIRONMENTS ------------------------------
+// Reference: EngineSiamese.sample (tneq_qc/core/engine_siamese.py:740-915) runs, for every qubit q, one full forward
+// at batch num_samples x grid_size (grid expansion :802-822, forward :842-847, inverse CDF :855-905): the work on
+// the qubits < q (already sampled) and > q (identity measurements) is redone for every grid point and every q.
+// Here one thread owns one sample and walks the chain ONCE:
+//   * left environment env (K x K, registers): the sweep over the sampled qubits, advanced by one chain_step per qubit;
+//   * right environments R_q (K x K, shared by all samples: the later qubits are measured with the identity), built
+//     once per CTA from the back of the chain and stored folded with the core, LR_q[h,g,f] = sum_j Ls_q[h,g,j] R_{q+1}[j,f];
+//   * the value is linear in the measurement matrix of qubit q: value(M) = sum_{e,g} C[e,g] M[e,g] with
+//     C[e,g] = sum_{h,c,f} env[h,c] Ls_q[c,e,f] LR_q[h,g,f] (2 K^4 multiply-adds), so a grid point costs K^2
+//     multiply-adds instead of a contraction of the whole network;
+//   * density = value clamped at 0 (abs_square is the identity for real dtypes, then clamp, :858-862), running sum =
+//     cumsum, divided by (total + 1e-10),
+//     index = #(cdf < u) clamped to G - 2, linear interpolation between the grid points idx and idx + 1 exactly as
+//     :884-901 (including its extrapolation quirk: cdf[idx] is the first value NOT below u);
+//   * the sampled value's matrix phi(y) phi(y)^T (generate_data, :133-254) is formed in registers.
+// The uniform numbers are drawn by the caller in the reference's order (one (S,1) draw per qubit).
+template <int K>
+__global__ void __launch_bounds__(CHAIN_THREADS)
+tnq_chain_sample_kernel(const __grid_constant__ ChainArgs a, long long S, int G, const float* __restrict__ grid_x,
+                        const float* __restrict__ mx_grid, int grid_in_smem, const float* __restrict__ u, HermiteW hw,
+                        float* __restrict__ samples) {
+    constexpr int K2 = K * K, K3 = K * K * K;
+    extern __shared__ float sm[];
+    const int n = a.n;
+    float* Ls = sm;                                   // [n-1][K3]
+    float* LR = Ls + (n - 1) * K3;                    // [n-1][K3]: LR_q[h][g][f]
+    float* R = LR + (n - 1) * K3;                     // [K2] scratch: R_{q+1}[j][f]
+    float* mg_s = R + K2;                             // [G][K2] when it fits
+    for (int i = threadIdx.x; i < (n - 1) * K3; i += blockDim.x) {
+        const int q = i / K3, r = i % K3, c = r / K2, e = (r / K) % K, f = r % K;
+        float s = 0.f;
+        for (int d = 0; d < K; ++d) s = fmaf(__ldg(a.core[q] + ((c * K + d) * K + e) * K + f), __ldg(a.state[q + 1] + d), s);
+        Ls[i] = s;
+    }
+    if (threadIdx.x < K2) R[threadIdx.x] = (threadIdx.x / K == threadIdx.x % K) ? 1.f : 0.f;     // R_{n-1} = identity
+    if (grid_in_smem)
+        for (int i = threadIdx.x; i < G * K2; i += blockDim.x) mg_s[i] = __ldg(mx_grid + i);
+    __syncthreads();
+    for (int q = n - 2; q >= 0; --q) {
+        const float* L = Ls + q * K3;
+        if (threadIdx.x < K3) {                       // LR_q[h][g][f] = sum_j Ls_q[h][g][j] R_{q+1}[j][f]
+            const int hg = threadIdx.x / K, f = threadIdx.x % K;
+            float s = 0.f;
+            for (int j = 0; j < K; ++j) s = fmaf(L[hg * K + j], R[j * K + f], s);
+            LR[q * K3 + threadIdx.x] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < K2) {                       // R_q[h][c] = sum_{e,f} Ls_q[c][e][f] LR_q[h][e][f]
+            const int h = threadIdx.x / K, c = threadIdx.x % K;
+            float s = 0.f;
+            for (int ef = 0; ef < K2; ++ef) s = fmaf(L[c * K2 + ef], LR[q * K3 + h * K2 + ef], s);
+            R[threadIdx.x] = s;
+        }
+        __syncthreads();
+    }
+    const float* mg = grid_in_smem ? mg_s : mx_grid;
+    float s0[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) s0[i] = __ldg(a.state[0] + i);
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < S; b += (long long)gridDim.x * blockDim.x) {
+        float env[K][K];
+#pragma unroll
+        for (int h = 0; h < K; ++h)
+#pragma unroll
+            for (int c = 0; c < K; ++c) env[h][c] = s0[h] * s0[c];
+        for (int q = 0; q < n; ++q) {
+            float C[K][K];                            // value(M) = sum C[e][g] M[e][g]
+            if (q < n - 1) {
+                const float* L = Ls + q * K3;
+                const float* W = LR + q * K3;
+                float T1[K][K][K];                    // [h][e][f]
+#pragma unroll
+                for (int h = 0; h < K; ++h)
+#pragma unroll
+                    for (int e = 0; e < K; ++e)
+#pragma unroll
+                        for (int f = 0; f < K; ++f) {
+                            float s = 0.f;
+#pragma unroll
+                            for (int c = 0; c < K; ++c) s = fmaf(env[h][c], L[(c * K + e) * K + f], s);
+                            T1[h][e][f] = s;
+                        }
+#pragma unroll
+                for (int e = 0; e < K; ++e)
+#pragma unroll
+                    for (int g = 0; g < K; ++g) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int h = 0; h < K; ++h)
+#pragma unroll
+                            for (int f = 0; f < K; ++f) s = fmaf(T1[h][e][f], W[(h * K + g) * K + f], s);
+                        C[e][g] = s;
+                    }
+            } else {                                  // "acd,adc->a": value = sum env[c][d] M[d][c]
+#pragma unroll
+                for (int e = 0; e < K; ++e)
+#pragma unroll
+                    for (int g = 0; g < K; ++g) C[e][g] = env[g][e];
+            }
+            // pass 1: the total of the densities (the last entry of the cumulative sum)
+            float total = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < G; ++i) {
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < K2; ++k) v = fmaf(C[k / K][k % K], mg[i * K2 + k], v);
+                total += fmaxf(v, 0.f);
+            }
+            const float denom = total + 1e-10f;
+            const float uu = __ldg(u + b * n + q);
+            // pass 2: idx = #(cdf < u); c0 = cdf[idx], c1 = cdf[idx + 1] after clamping idx to G - 2
+            float run = 0.f, prev = 0.f, cur = 0.f, c0 = 0.f, c1 = 0.f;
+            int idx = 0, state = 0;                   // state 0: still below u, 1: c0 taken, 2: c1 taken
+            for (int i = 0; i < G; ++i) {
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < K2; ++k) v = fmaf(C[k / K][k % K], mg[i * K2 + k], v);
+                run += fmaxf(v, 0.f);
+                prev = cur;
+                cur = run / denom;
+                if (state == 1) c1 = cur, state = 2;
+                if (state == 0) {
+                    if (cur < uu) ++idx;
+                    else c0 = cur, state = 1;
+                }
+            }
+            if (idx > G - 2) idx = G - 2, c0 = prev, c1 = cur;        // (also: first value not below u was the last one)
+            const float x0 = __ldg(grid_x + idx), x1 = __ldg(grid_x + idx + 1);
+            const float y = x0 + (uu - c0) / (c1 - c0 + 1e-10f) * (x1 - x0);
+            samples[b * n + q] = y;
+            if (q < n - 1) {
+                float phi[K], M[K][K];
+                hermite_phi<K>(y, hw, phi);
+#pragma unroll
+                for (int e = 0; e < K; ++e)
+#pragma unroll
+                    for (int g = 0; g < K; ++g) M[e][g] = phi[e] * phi[g];
+                chain_step<K>(env, Ls + q * K3, M);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -922,6 +1067,57 @@ int tnq_mps_chain_x(int K, int n, const float* const* cores, const float* const*
 #undef TNQ_CHAIN_X
     e = cudaGetLastError();
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_mps_chain_x launch");
+    return 0;
+}
+
+/* sample() with prefix environments for single-layer MPS networks (see tnq_chain_sample_kernel):
+ *   grid_x[G], mx_grid[G][K][K] (the grid's measurement matrices), u[S][n] uniform numbers (qubit q of sample s at
+ *   u[s * n + q]), weights[K] (host: generate_data's Hermite weights) -> samples[S][n]. */
+int tnq_mps_chain_sample(int K, int n, const float* const* cores, const float* const* states, int64_t S, int G,
+                         const float* grid_x, const float* mx_grid, const float* u, const float* weights, float* samples,
+                         void* stream) {
+    if (n < 2 || n > MAXQ) return tnq_internal_fail("tnq_mps_chain_sample: between 2 and " + std::to_string(MAXQ) + " qubits");
+    if (K < 2 || K > 4) return tnq_internal_fail("tnq_mps_chain_sample: edge rank must be 2, 3 or 4");
+    if (!cores || !states || !grid_x || !mx_grid || !u || !weights || !samples || S <= 0 || G < 2)
+        return tnq_internal_fail("tnq_mps_chain_sample: bad arguments");
+    ChainArgs a;
+    a.n = n;
+    for (int q = 0; q < n; ++q) {
+        a.state[q] = states[q];
+        a.mx[q] = nullptr;
+        a.mx_stride[q] = 0;
+        a.core[q] = q < n - 1 ? cores[q] : nullptr;
+        a.grad[q] = nullptr;
+        if (!states[q] || (q < n - 1 && !cores[q])) return tnq_internal_fail("tnq_mps_chain_sample: null pointer at qubit " + std::to_string(q));
+    }
+    HermiteW hw;
+    for (int i = 0; i < 4; ++i) hw.w[i] = i < K ? weights[i] : 0.f;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int K2 = K * K, K3 = K * K * K;
+    const size_t base = sizeof(float) * ((size_t)2 * (n - 1) * K3 + K2);
+    const size_t gridb = sizeof(float) * (size_t)G * K2;
+    const int in_smem = base + gridb <= 160 * 1024 ? 1 : 0;
+    const size_t smem = base + (in_smem ? gridb : 0);
+    long long want = (S + CHAIN_THREADS - 1) / CHAIN_THREADS;
+    const long long cap = (long long)sms * 2;
+    const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    cudaError_t e = cudaSuccess;
+#define TNQ_CHAIN_SAMPLE(KK)                                                                                          \
+    e = cudaFuncSetAttribute(tnq_chain_sample_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(chain sample)");                     \
+    tnq_chain_sample_kernel<KK><<<grid, CHAIN_THREADS, smem, st>>>(a, S, G, grid_x, mx_grid, in_smem, u, hw, samples);
+    switch (K) {
+        case 2: TNQ_CHAIN_SAMPLE(2) break;
+        case 3: TNQ_CHAIN_SAMPLE(3) break;
+        default: TNQ_CHAIN_SAMPLE(4) break;
+    }
+#undef TNQ_CHAIN_SAMPLE
+    tnq_internal_count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_mps_chain_sample launch");
     return 0;
 }
 

@@ -196,6 +196,57 @@ def test_sampling_linear_method_equals_grid_method(built_lib):
         assert (out["linear"] - out["grid"]).abs().max().item() < 2e-3, kind
 
 
+def test_sampling_prefix_environments_equal_contraction_methods(built_lib):
+    """sample(method='prefix') -- one kernel launch, a thread per sample, left environment cached in
+    registers, shared right environments (tnq_mps_chain_sample) -- draws the same samples from the same random
+    numbers as the reference's procedure (method='grid': one full forward per qubit at batch S x G) and as
+    method='linear', for K = 2, 3, 4, TNTensor and plain cores; 'auto' picks it for a single-layer MPS and
+    falls back to 'linear' (same draws) elsewhere."""
+    for n, K, G, S in ((6, 3, 60, 64), (4, 2, 33, 70), (5, 4, 50, 40), (2, 3, 25, 9)):
+        graph = _graph("mps", n, K)
+        be, eng = _engine("float32", K, built_lib)
+        torch.manual_seed(5 + n)
+        names, table, nq = oc.parse_graph(graph)
+        cores = oc.random_cores(table)
+        q = tneq_b200.QCTN(graph, backend=be)
+        for k, v in cores.items():
+            q.cores_weights[k] = v.cuda()
+        st = [s.cuda() for s in oc.unit_states(nq, K)]
+        out = {}
+        launches = {}
+        for method in ("grid", "linear", "prefix", "auto"):
+            torch.manual_seed(77)
+            torch.cuda.manual_seed(77)
+            l0 = tneq_b200._lib.launch_count()
+            out[method] = eng.sample(q, st, num_samples=S, K=K, bounds=[-5, 5], grid_size=G, method=method)
+            launches[method] = tneq_b200._lib.launch_count() - l0
+        assert tuple(out["prefix"].shape) == (S, nq)
+        assert launches["prefix"] == 1 and launches["auto"] == 1 and launches["grid"] >= nq
+        assert (out["prefix"] >= -5).all() and (out["prefix"] <= 5).all()
+        # the inverse CDF is continuous in the densities: float32 round-off in the running sums moves a sample by
+        # ~1e-6 of the grid spacing, a flipped `cdf < u` comparison leaves the interpolated value continuous
+        # (the bulk agrees to ~1e-6; where a grid cell carries almost no probability the reference's own formula
+        # (u - c0) / (c1 - c0 + 1e-10) divides two round-off-sized numbers, hence a bound in units of the cell)
+        cell = 10.0 / (G - 1)
+        for other in ("grid", "linear"):
+            diff = (out["prefix"] - out[other]).abs()
+            assert diff.median().item() < 1e-5 and diff.max().item() < 0.05 * cell, (n, K, other, diff.max().item())
+        assert torch.equal(out["auto"], out["prefix"])
+    # another network family: 'auto' = 'linear', with the draws made up front
+    graph = _graph("merged", 4, 3)
+    be, eng = _engine("float32", 3, built_lib)
+    q = tneq_b200.QCTN(graph, backend=be)
+    st = [s.cuda() for s in oc.unit_states(4, 3)]
+    res = {}
+    for method in ("linear", "auto"):
+        torch.manual_seed(3)
+        torch.cuda.manual_seed(3)
+        res[method] = eng.sample(q, st, num_samples=32, K=3, bounds=[-5, 5], grid_size=30, method=method)
+    assert (res["auto"] - res["linear"]).abs().max().item() < 1e-5
+    with pytest.raises(NotImplementedError):
+        eng.sample(q, st, num_samples=4, K=3, grid_size=10, method="prefix")
+
+
 def test_large_batch_and_ragged_tail(built_lib):
     """Batch sizes that are not a multiple of the tile, and one bigger than a wave."""
     K, n = 3, 8
