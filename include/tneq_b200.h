@@ -170,6 +170,17 @@ int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t M, int64_t
 /* Launch resources of one variant of the GEMM kernel: out[4] = {registers per thread, max threads per block,
  * static shared bytes, threads per block the launch uses}. */
 int tnq_gemm_kernel_attrs(int aligned, int smallk, int* out);
+/*
+ * The same GEMM with the index permutation of the A operand done by the TMA unit: A is a strided 4-level VIEW
+ * (rows m = r1 * R0 + r0, contraction index k = k1 * K0 + k0, element at A + r1*sR1 + r0*sR0 + k1*sK1 + k0, strides in
+ * floats), e.g. the B x chi^3 intermediate [b, i, j, (k,l)] of the bond-64 sweep read as rows (b, j) x K (i, k, l)
+ * without the explicit transposition the reference's einsum performs (permute + reshape + bmm,
+ * tneq_qc/contractor/greedy_strategy.py:940,959).  B: N x K row major (ldb); C: M x N row major (ldc).
+ * Returns -2 WITHOUT launching when the view is not expressible as a tensor map (alignment; K0 % 32; R0 neither a
+ * multiple nor a divisor of 128; K <= 256): the caller then transposes with tnq_permute_f32 and calls tnq_gemm_tf32x3.
+ */
+int tnq_gemm_tf32x3_view(const float* A, int64_t R1, int64_t R0, int64_t sR1, int64_t sR0, int64_t K1, int64_t K0,
+                         int64_t sK1, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t N, void* stream);
 
 /*
  * Index permutation / merge / split of a dense fp32 tensor (what torch.einsum does around every

@@ -55,6 +55,49 @@ class GemmPathRunner:
                                             M, N, K, lda, ldb, ldc, batch, sA, sB, sC, int(accumulate), self._stream()))
         self.flops += 2.0 * M * N * K * batch
 
+    def _gemm_view(self, A, view, Bm, C, N, ldb, ldc):
+        """C = A_view x Bm^T with the permutation of A done by the TMA unit (tnq_gemm_tf32x3_view).  False: the
+        view is not expressible as a tensor map; nothing was launched."""
+        R1, R0, sR1, sR0, K1, K0, sK1 = view
+        rc = self.lib.tnq_gemm_tf32x3_view(c_void_p(A.data_ptr()), R1, R0, sR1, sR0, K1, K0, sK1, c_void_p(Bm.data_ptr()),
+                                           ldb, c_void_p(C.data_ptr()), ldc, N, self._stream())
+        if rc == -2:
+            return False
+        _lib.check(rc)
+        self.flops += 2.0 * R1 * R0 * N * K1 * K0
+        return True
+
+    def _strided_view(self, layout: List[int], rows: List[int], cols: List[int], B: int):
+        """`layout` read as rows x cols WITHOUT a copy, when memory order alternates as [rows][cols][rows][cols]
+        (outer to inner; leading groups may be missing): (R1, R0, sR1, sR0, K1, K0, sK1) and the row order, or
+        None.  cols must already be in memory order (they are: _tail_order)."""
+        rs, cs = set(rows), set(cols)
+        if [i for i in layout if i in cs] != list(cols) or len(rs) + len(cs) != len(layout):
+            return None
+        segs = []                                    # [(is_col, [indices])] outer -> inner
+        for i in layout:
+            c = i in cs
+            if segs and segs[-1][0] == c:
+                segs[-1][1].append(i)
+            else:
+                segs.append((c, [i]))
+        if not segs or not segs[-1][0] or len(segs) not in (3, 4):
+            return None                              # 1-2 groups: no transposition needed; 5+: not a 4-level view
+        strides, s = {}, 1
+        for i in reversed(layout):
+            strides[i] = s
+            s *= self._extent(i, B)
+        size = lambda idx: self._size(idx, B)
+        k0, r0 = segs[-1][1], segs[-2][1]
+        k1 = segs[-3][1]
+        r1 = segs[-4][1] if len(segs) == 4 else []
+        view = (size(r1), size(r0), strides[r1[-1]] if r1 else 0, strides[r0[-1]], size(k1), size(k0), strides[k1[-1]])
+        R1, R0, sR1, sR0, K1, K0, sK1 = view
+        # what tnq_gemm_tf32x3_view can describe to the TMA unit (it re-checks, plus the pointer alignment)
+        if K0 % 32 or not (R0 % 128 == 0 or 128 % R0 == 0) or K1 * K0 <= 256 or sR1 % 4 or sR0 % 4 or sK1 % 4:
+            return None
+        return view, r1 + r0
+
     # ---- layouts --------------------------------------------------------------------------
     def _extent(self, i, B):
         return B if i == BATCH else self.g.dims[i]
@@ -219,8 +262,22 @@ class GemmPathRunner:
             p, q, tp, Lp, tq, Lq, pf, qf = q, p, tq, Lq, tp, Lp, qf, pf
         lead = [BATCH] if p.batched else []
         korder = self._tail_order(Lp, shared)
-        A, rows_a = self._arrange(tp, Lp, lead + pf, korder, NS)
         K = self._size(shared, NS)
+        if not q.batched:
+            # the A operand read in place through a 4-D tensor map when its memory order is [rows][k][rows][k]
+            sv = self._strided_view(Lp, lead + pf, korder, NS)
+            if sv is not None:
+                view, rows_a = sv
+                kn = self._knext.get(n.id, set())
+                want_b = [i for i in qf if i not in kn] + [i for i in qf if i in kn]
+                cur_b = [i for i in Lq if i in set(qf)]
+                Bm, rows_b = self._arrange(tq, Lq, want_b, korder, NS, exact=(want_b != cur_b))
+                M, N = self._size(rows_a, NS), self._size(rows_b, NS)
+                C = torch.empty((M, N), dtype=torch.float32, device=self.device)
+                if self._gemm_view(tp, view, Bm, C, N, K, N):
+                    out_layout = rows_a + rows_b
+                    return C.reshape([self._extent(i, NS) for i in out_layout] or [1]), out_layout
+        A, rows_a = self._arrange(tp, Lp, lead + pf, korder, NS)
         if q.batched:
             # both per-sample: one GEMM per sample (batch in grid.z)
             Bm, rows_b = self._arrange(tq, Lq, [BATCH] + qf, korder, NS)

@@ -398,6 +398,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 // UMMA shared-memory descriptor, K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
 // (SBO); LBO is not used by swizzled K-major layouts; a K=8 step advances the start address by 32 bytes inside
 // the swizzle atom (the hardware applies the XOR to the absolute address bits: tiles are 1024-byte aligned).
@@ -431,7 +437,10 @@ template <int NRAW, int NLO, bool SOLO>
 __global__ void __maxnreg__(SOLO ? 128 : 168)
 tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
                     long long M, long long N, long long K, long long ldc, long long strideC, int zA, int zB, int accumulate,
-                    int rewrite_hi, int splitk) {
+                    int rewrite_hi, int splitk, int a_r0, int a_kdiv) {
+    // a_r0 > 0: A is a strided VIEW described by a 4-D tensor map (k0, r0, k1, r1) -- rows m = r1 * a_r0 + r0,
+    // contraction index k = k1 * (32 a_kdiv) + k0: the index permutation an explicit transposition kernel would
+    // do is done by the TMA unit while it fills the tile (tnq_gemm_tf32x3_view)
     static_assert(!SOLO || NLO == 1, "the solo variant serialises conversion and MMA");
     static_assert(NRAW >= NLO, "done[] is indexed by the raw stage");
     constexpr uint32_t NCOLS = (NLO + 1) * BN <= 256 ? 256u : 512u;
@@ -479,7 +488,12 @@ tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int sr = kb % NRAW;
         const uint32_t dst = raw0 + (uint32_t)sr * RAW_BYTES, bar = full_raw0 + 8 * sr;
         mbar_expect_tx(bar, RAW_BYTES);
-        tma_load_3d(dst, &tmA, bar, (kb0 + kb) * BK, (int)m0, za);
+        if (a_r0 > 0) {
+            const int kk = kb0 + kb;
+            tma_load_4d(dst, &tmA, bar, (kk % a_kdiv) * BK, a_r0 >= BM ? (int)(m0 % a_r0) : 0, kk / a_kdiv, (int)(m0 / a_r0));
+        } else {
+            tma_load_3d(dst, &tmA, bar, (kb0 + kb) * BK, (int)m0, za);
+        }
         tma_load_3d(dst + TILE_BYTES, &tmB, bar, (kb0 + kb) * BK, (int)n0, zb);
     };
 
@@ -610,9 +624,27 @@ bool make_operand_map(CUtensorMap* map, const float* base, long long rows, long 
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// (k0, r0, k1, r1) view: element (m = r1 * R0 + r0, k = k1 * K0 + k0) at base + r1 sR1 + r0 sR0 + k1 sK1 + k0
+bool make_view_map(CUtensorMap* map, const float* base, long long R1, long long R0, long long sR1, long long sR0,
+                   long long K1, long long K0, long long sK1) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    if (((uintptr_t)base & 15) || (sR1 & 3) || (sR0 & 3) || (sK1 & 3) || K0 % BK || R0 <= 0 || R1 <= 0 || K1 <= 0) return false;
+    if (!(R0 % BM == 0 || BM % R0 == 0)) return false;
+    if (sR0 <= 0 || (R1 > 1 && sR1 <= 0) || (K1 > 1 && sK1 <= 0)) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)K0, (cuuint64_t)R0, (cuuint64_t)K1, (cuuint64_t)R1};
+    const cuuint64_t strides[3] = {(cuuint64_t)sR0 * 4, (cuuint64_t)(K1 > 1 ? sK1 : K0) * 4, (cuuint64_t)(R1 > 1 ? sR1 : sR0 * R0) * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(R0 >= BM ? BM : R0), 1, (cuuint32_t)(R0 >= BM ? 1 : BM / R0)};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NRAW, int NLO, bool SOLO>
 int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long M, long long N, long long K, long long ldc,
-               long long strideC, long long batch, int zA, int zB, int accumulate, int rewrite_hi, cudaStream_t st) {
+               long long strideC, long long batch, int zA, int zB, int accumulate, int rewrite_hi, cudaStream_t st,
+               int a_r0 = 0, int a_kdiv = 1) {
     // split-K by two when a long k-loop would leave more than half of the SMs without a tile (the core-gradient GEMMs
     // of the bond-64 sweep: 64 tiles, K = 16 384): C is zeroed, both halves add atomically
     int splitk = 1;
@@ -630,7 +662,7 @@ int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(gemm tma)");
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)(splitk > 1 ? splitk : batch));
-    kern<<<grid, SOLO ? PRODUCERS : PRODUCERS + 64, smem, st>>>(ta, tb, C, M, N, K, ldc, strideC, zA, zB, accumulate, rewrite_hi, splitk);
+    kern<<<grid, SOLO ? PRODUCERS : PRODUCERS + 64, smem, st>>>(ta, tb, C, M, N, K, ldc, strideC, zA, zB, accumulate, rewrite_hi, splitk, a_r0, a_kdiv);
     tnq_internal_count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_gemm_tf32x3 (TMA) launch");
@@ -688,4 +720,20 @@ extern "C" int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t
     e = cudaGetLastError();
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_gemm_tf32x3 launch");
     return 0;
+}
+
+/* C (M x N, row major, ldc) = A_view * B^T with A a strided 4-level VIEW of a tensor in HBM (see tneq_b200.h):
+ * rows m = r1 * R0 + r0, contraction index k = k1 * K0 + k0, element at A + r1 sR1 + r0 sR0 + k1 sK1 + k0.
+ * Returns TNQ_NOT_EXPRESSIBLE (-2) without launching when the view cannot be described to the TMA unit (alignment,
+ * K0 not a multiple of 32, R0 neither a multiple nor a divisor of 128, K <= 256): the caller transposes explicitly. */
+extern "C" int tnq_gemm_tf32x3_view(const float* A, int64_t R1, int64_t R0, int64_t sR1, int64_t sR0, int64_t K1, int64_t K0,
+                                    int64_t sK1, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t N, void* stream) {
+    if (!A || !B || !C || N <= 0) return tnq_internal_fail("tnq_gemm_tf32x3_view: bad arguments");
+    const long long M = R1 * R0, K = K1 * K0;
+    static const bool no_tma = getenv("TNQ_GEMM_NO_TMA") != nullptr || getenv("TNQ_GEMM_NO_VIEW") != nullptr;
+    if (no_tma || K <= 256 || M > 0x7fffffffLL) return -2;
+    CUtensorMap ta, tb;
+    int zB = 0;
+    if (!make_view_map(&ta, A, R1, R0, sR1, sR0, K1, K0, sK1) || !make_operand_map(&tb, B, N, K, ldb, 1, 0, &zB)) return -2;
+    return launch_tma<4, 2, false>(ta, tb, C, M, N, K, ldc, 0, 1, 0, 0, 0, 0, (cudaStream_t)stream, (int)R0, (int)(K0 / BK));
 }

@@ -72,3 +72,30 @@ def test_gemm_unaligned_shapes(built_lib):
         torch.cuda.synchronize()
         ref = A.double() @ B.double().transpose(-1, -2)
         assert ((C.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+@pytest.mark.parametrize("R1,R0,K1,K0,N", [(3, 64, 5, 64, 128), (2, 256, 3, 128, 72), (5, 32, 9, 32, 40), (1, 128, 4, 96, 130),
+                                           (256, 64, 4, 128, 128)])
+def test_gemm_strided_view_operand(R1, R0, K1, K0, N, built_lib):
+    """tnq_gemm_tf32x3_view: the A operand is read in place through a 4-D tensor map -- memory order
+    [r1][k1][r0][k0], rows (r1, r0), contraction index (k1, k0) -- i.e. the transposition is done by the TMA
+    unit; against float64 of the explicitly permuted operand (tile tails in M through zero fill)."""
+    from tneq_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(R1 * 100 + K1)
+    X = torch.randn(R1, K1, R0, K0, device="cuda")
+    B = torch.randn(N, K1 * K0, device="cuda")
+    M, K = R1 * R0, K1 * K0
+    C = torch.empty(M, N, device="cuda")
+    rc = lib.tnq_gemm_tf32x3_view(ctypes.c_void_p(X.data_ptr()), R1, R0, X.stride(0), X.stride(2), K1, K0, X.stride(1),
+                                  ctypes.c_void_p(B.data_ptr()), K, ctypes.c_void_p(C.data_ptr()), N, N,
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    ref = X.permute(0, 2, 1, 3).reshape(M, K).double() @ B.double().T
+    err = ((C.double() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1e-5, err
+    # not expressible (K0 not a multiple of 32): refused without a launch, the caller transposes
+    assert lib.tnq_gemm_tf32x3_view(ctypes.c_void_p(X.data_ptr()), R1, R0, X.stride(0), X.stride(2), K1, K0 - 4, X.stride(1),
+                                    ctypes.c_void_p(B.data_ptr()), K, ctypes.c_void_p(C.data_ptr()), N, N,
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == -2

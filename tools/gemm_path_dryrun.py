@@ -32,6 +32,12 @@ class FakeLib:
     def tnq_cplx_fold_f32(self, src, dst, k, dims, *rest):
         return self._elementwise("fold", dims, k)
 
+    def tnq_gemm_tf32x3_view(self, A, R1, R0, sR1, sR0, K1, K0, sK1, B, ldb, C, ldc, N, stream):
+        ok = K0 % 32 == 0 and (R0 % 128 == 0 or 128 % R0 == 0) and K1 * K0 > 256 and not (sR1 % 4 or sR0 % 4 or sK1 % 4)
+        if ok:
+            self.log.append(("gemm", 2.0 * R1 * R0 * N * K1 * K0, R1 * R0, N, K1 * K0, 1, ("view", R1, R0, sR1, sR0, K1, K0, sK1)))
+        return 0 if ok else -2
+
 
 class DryRunner(gemm_path.GemmPathRunner):
     def __init__(self, graph):
@@ -48,6 +54,12 @@ class DryRunner(gemm_path.GemmPathRunner):
             n *= d
         self.log.append(("permute", n * 8, list(out_dims), list(src_strides), vec))
         return torch.empty(tuple(out_dims), dtype=torch.float32, device="meta")
+
+    def _gemm_view(self, A, view, Bm, C, N, ldb, ldc):
+        rc = self.lib.tnq_gemm_tf32x3_view(None, *view, None, ldb, None, ldc, N, None)
+        if rc == 0:
+            self.flops += 2.0 * view[0] * view[1] * N * view[4] * view[5]
+        return rc == 0
 
     def _gemm(self, A, B, C, M, N, K, lda, ldb, ldc, batch=1, sA=0, sB=0, sC=0, accumulate=False):
         self.log.append(("gemm", 2.0 * M * N * K * batch, M, N, K, batch, getattr(self, "_cur", None)))
@@ -92,7 +104,7 @@ def main():
                 print(f"  node {nn.id:4d} {nn.role:4s} contract     {e[0]:8s} {e[1] / 1e6:10.1f} MB  dims {e[2]} strides {e[3]} vec {e[4]}")
             else:
                 print(f"  node {nn.id:4d} {nn.role:4s} contract     GEMM     {e[1] / 1e9:10.2f} GF  M {e[2]} N {e[3]} K {e[4]} batch {e[5]}"
-                      f"  p{'(b)' if p.batched else ''} {lay[p.id]} x q{'(b)' if qn.batched else ''} {lay[qn.id]} -> {out[1]} reduce_batch={nn.reduce_batch}")
+                      f"  p{'(b)' if p.batched else ''} {lay[p.id]} x q{'(b)' if qn.batched else ''} {lay[qn.id]} -> {out[1]} reduce_batch={nn.reduce_batch}{' VIEW ' + str(e[6][1:]) if isinstance(e[6], tuple) and e[6] and e[6][0] == 'view' else ''}")
         return out
 
     r._lin, r._contract = lin, con
