@@ -435,7 +435,8 @@ __device__ __forceinline__ void issue_kblock_tma(uint32_t raw, uint32_t lo, uint
 // two CTAs per SM so that one tile's epilogue overlaps the other's main loop.
 template <int NRAW, int NLO, bool SOLO>
 __global__ void __maxnreg__(SOLO ? 128 : 168)
-tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, int tma_store, float* __restrict__ C,
                     long long M, long long N, long long K, long long ldc, long long strideC, int zA, int zB, int accumulate,
                     int rewrite_hi, int splitk, int a_r0, int a_kdiv) {
     // a_r0 > 0: A is a strided VIEW described by a 4-D tensor map (k0, r0, k1, r1) -- rows m = r1 * a_r0 + r0,
@@ -464,6 +465,7 @@ tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+        if (tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmC) : "memory");
     }
     constexpr int ALLOC_WARP = SOLO ? 1 : PRODUCERS / 32;
     if (warp == ALLOC_WARP) {
@@ -557,8 +559,39 @@ tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             have = true;
         }
         drain_add(tmem_corr - tmem_base + tlane, sum, false);
-        float* xpose = reinterpret_cast<float*>(smem + (smem_base - smem_u32(smem))) + warp * (32 * 33);   // the rings are idle now
-        store_tile(sum, xpose, lane, C, ldc, m0 + quad * 32, n0 + chalf * 64, M, N, accumulate);
+        if (tma_store && accumulate == 0) {
+            // the tile leaves through the TMA unit (SASS UTMASTG): every thread parks its 64 columns in four staging
+            // boxes of 128 rows x 32 floats in the 128-byte swizzle (the rings are idle now; 4-way bank conflicts =
+            // the minimum for 512 bytes per warp instruction), one thread per column half issues the two stores;
+            // rows / columns beyond M / N are clipped by the tensor map
+            const uint32_t stage = smem_base;
+            const int row = quad * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const int box = chalf * 2 + (c >> 3), ch = c & 7;
+                const uint32_t at = stage + (uint32_t)box * TILE_BYTES + (uint32_t)row * 128u + (uint32_t)((ch ^ (row & 7)) * 16);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(at), "f"(sum[4 * c]), "f"(sum[4 * c + 1]),
+                             "f"(sum[4 * c + 2]), "f"(sum[4 * c + 3])
+                             : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (chalf == 0) asm volatile("bar.sync 1, 128;" ::: "memory");      // the four warps of this column half
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if ((warp & 3) == 0 && lane == 0) {
+#pragma unroll
+                for (int bx = 0; bx < 2; ++bx) {
+                    const int box = chalf * 2 + bx;
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)&tmC),
+                                 "r"(stage + (uint32_t)box * TILE_BYTES), "r"((int)n0 + box * 32), "r"((int)m0), "r"((int)blockIdx.z)
+                                 : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory is read before the CTA retires
+            }
+        } else {
+            float* xpose = reinterpret_cast<float*>(smem + (smem_base - smem_u32(smem))) + warp * (32 * 33);   // the rings are idle now
+            store_tile(sum, xpose, lane, C, ldc, m0 + quad * 32, n0 + chalf * 64, M, N, accumulate);
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else if (!SOLO && warp == PRODUCERS / 32) {
         // ---------------- MMA issuer ----------------
@@ -641,6 +674,22 @@ bool make_view_map(CUtensorMap* map, const float* base, long long R1, long long 
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// (n, m, batch) view of C for the TMA store: 128 x 32 boxes in the 128-byte swizzle
+bool make_c_map(CUtensorMap* map, float* base, long long M, long long N, long long ldc, long long batch, long long strideC) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    if (((uintptr_t)base & 15) || (ldc & 3) || ldc < N || M > 0x7fffffffLL || N > 0x7fffffffLL) return false;
+    if (batch > 1 && ((strideC & 3) || strideC < M * ldc || batch > 0x7fffffffLL)) return false;
+    long long s2 = batch > 1 ? strideC : M * ldc;
+    s2 = (s2 + 3) & ~3LL;
+    const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)(batch > 1 ? batch : 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)ldc * 4, (cuuint64_t)s2 * 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)BM, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NRAW, int NLO, bool SOLO>
 int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long M, long long N, long long K, long long ldc,
                long long strideC, long long batch, int zA, int zB, int accumulate, int rewrite_hi, cudaStream_t st,
@@ -657,12 +706,17 @@ int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long
                                   : cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, st);
         if (e0 != cudaSuccess) return tnq_internal_cuda_fail(e0, "cudaMemsetAsync(gemm split-K)");
     }
+    // the tile leaves through a TMA store when C can be described by a tensor map and is written (not added to)
+    CUtensorMap tc;
+    static const bool no_store = getenv("TNQ_GEMM_NO_TMA_STORE") != nullptr;
+    const int tma_store = (!no_store && splitk == 1 && !accumulate && make_c_map(&tc, C, M, N, ldc, batch, strideC)) ? 1 : 0;
+    if (!tma_store) tc = ta;                                       // (a valid descriptor; never used)
     const size_t smem = (size_t)(NRAW + NLO) * RAW_BYTES + 1024;
     auto kern = tnq_gemm_tma_kernel<NRAW, NLO, SOLO>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(gemm tma)");
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)(splitk > 1 ? splitk : batch));
-    kern<<<grid, SOLO ? PRODUCERS : PRODUCERS + 64, smem, st>>>(ta, tb, C, M, N, K, ldc, strideC, zA, zB, accumulate, rewrite_hi, splitk, a_r0, a_kdiv);
+    kern<<<grid, SOLO ? PRODUCERS : PRODUCERS + 64, smem, st>>>(ta, tb, tc, tma_store, C, M, N, K, ldc, strideC, zA, zB, accumulate, rewrite_hi, splitk, a_r0, a_kdiv);
     tnq_internal_count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_gemm_tf32x3 (TMA) launch");
