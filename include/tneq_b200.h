@@ -169,6 +169,16 @@ int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t M, int64_t
                     int accumulate, void* stream);
 /* Launch resources of one variant of the GEMM kernel: out[4] = {registers per thread, max threads per block,
  * static shared bytes, threads per block the launch uses}. */
+/*
+ * Contraction of a big tensor with a tiny one over ONE index and the complex component -- the circuit-state operands
+ * of every greedy group ("cdef,...,d,i->...": Bs[c,e,f] = sum_d G[c,d,e,f] s[d], tneq_qc/contractor/greedy_strategy.py:690-990)
+ * at large bond dimension, complex data in the 2x2-real form -- and its adjoint, both in ONE pass over the big tensor
+ * (the generic route: a transposition of the 134 MB core plus a GEMM with two columns):
+ *   tnq_fold_vec_f32 : out[a, c, ro]  = sum_{d, ri} P[a, d, c, ri] * Q[d, ri, ro]      P [A][D][C][2], Q [D][2][2]
+ *   tnq_outer_acc_f32: T[a, d, c, ri] += sum_ro     P[a, c, ro]    * Q[d, ri, ro]      P [A][C][2],    T [A][D][C][2]
+ */
+int tnq_fold_vec_f32(const float* P, const float* Q, float* out, int64_t A, int64_t D, int64_t C, void* stream);
+int tnq_outer_acc_f32(const float* P, const float* Q, float* T, int64_t A, int64_t D, int64_t C, void* stream);
 int tnq_gemm_kernel_attrs(int aligned, int smallk, int* out);
 /*
  * The same GEMM with the index permutation of the A operand done by the TMA unit: A is a strided 4-level VIEW

@@ -67,6 +67,70 @@ class GemmPathRunner:
         self.flops += 2.0 * R1 * R0 * N * K1 * K0
         return True
 
+    # ---- big tensor x tiny tensor over one index (+ complex component): the circuit-state operands ----------------
+    def _small_partner(self, n: Node, val, lay):
+        """(big, small) operand nodes of `n` when one operand is a tiny non-batched rank-3 tensor [d, ri, ro] in its
+        own memory order (the 2x2-real expansion of a complex vector) and the other a non-batched tensor whose
+        innermost index is a complex component; else None."""
+        g = self.g
+        if n.reduce_batch:
+            return None
+        for big, small in ((g.nodes[n.p], g.nodes[n.q]), (g.nodes[n.q], g.nodes[n.p])):
+            if big.batched or small.batched or len(small.idx) != 3 or len(big.idx) < 2:
+                continue
+            if lay[small.id] != list(small.idx) or g.dims[small.idx[1]] != 2 or g.dims[small.idx[2]] != 2:
+                continue
+            if g.dims[lay[big.id][-1]] != 2 or not val[small.id].is_contiguous() or not val[big.id].is_contiguous():
+                continue
+            return big, small
+        return None
+
+    def _fold_vec(self, n: Node, val, lay):
+        """out[.., ro] = sum_{d, ri} big[.., d, .., ri] small[d, ri, ro] in one pass over `big` (tnq_fold_vec_f32)."""
+        pair = self._small_partner(n, val, lay)
+        if pair is None or n.acc_into >= 0:
+            return None
+        big, small = pair
+        g, L = self.g, lay[big.id]
+        d, ri, ro = small.idx
+        shared = set(big.idx) & set(small.idx)
+        if shared != {d, ri} or L[-1] != ri or d not in L[:-1]:
+            return None
+        j = L.index(d)
+        A, D, C = self._size(L[:j], 1), g.dims[d], self._size(L[j + 1:-1], 1)
+        out_layout = L[:j] + L[j + 1:-1] + [ro]
+        out = torch.empty([g.dims[i] for i in out_layout], dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.tnq_fold_vec_f32(c_void_p(val[big.id].data_ptr()), c_void_p(val[small.id].data_ptr()),
+                                             c_void_p(out.data_ptr()), A, D, C, self._stream()))
+        self.flops += 2.0 * A * D * C * 4
+        return out, out_layout
+
+    def _outer_acc(self, n: Node, val, lay) -> bool:
+        """target[.., d, .., ri] += sum_ro big[.., ro] small[d, ri, ro], accumulated in place in the target's memory
+        order (tnq_outer_acc_f32): the adjoint of _fold_vec, instead of GEMM (K = 2) + transposition + add."""
+        pair = self._small_partner(n, val, lay)
+        if pair is None or n.acc_into < 0:
+            return False
+        big, small = pair
+        g, L = self.g, lay[big.id]
+        d, ri, ro = small.idx
+        if set(big.idx) & set(small.idx) != {ro} or L[-1] != ro:
+            return False
+        T = list(n.idx)                              # the target's memory order
+        if T[-1] != ri or d not in T[:-1]:
+            return False
+        j = T.index(d)
+        if T[:j] + T[j + 1:-1] != L[:-1]:
+            return False
+        tgt = val[n.acc_into]
+        if not tgt.is_contiguous():
+            return False
+        A, D, C = self._size(T[:j], 1), g.dims[d], self._size(T[j + 1:-1], 1)
+        _lib.check(self.lib.tnq_outer_acc_f32(c_void_p(val[big.id].data_ptr()), c_void_p(val[small.id].data_ptr()),
+                                              c_void_p(tgt.data_ptr()), A, D, C, self._stream()))
+        self.flops += 2.0 * A * D * C * 4
+        return True
+
     def _strided_view(self, layout: List[int], rows: List[int], cols: List[int], B: int):
         """`layout` read as rows x cols WITHOUT a copy, when memory order alternates as [rows][cols][rows][cols]
         (outer to inner; leading groups may be missing): (R1, R0, sR1, sR0, K1, K0, sK1) and the row order, or
@@ -176,7 +240,10 @@ class GemmPathRunner:
             if n.kind == "lin":
                 out, out_layout = self._lin(n, val, lay, NS)
             else:
-                out, out_layout = self._contract(n, val, lay, NS)
+                if self._outer_acc(n, val, lay):
+                    continue
+                fused = self._fold_vec(n, val, lay)
+                out, out_layout = fused if fused is not None else self._contract(n, val, lay, NS)
             if n.acc_into >= 0:
                 # a contribution is declared in the target's memory order (its own labels: a core's
                 # L and R occurrences carry different index ids over the same buffer)

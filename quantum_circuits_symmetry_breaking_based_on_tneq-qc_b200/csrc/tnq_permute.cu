@@ -238,6 +238,53 @@ __global__ void __launch_bounds__(256) cplx_fold_kernel(const float* __restrict_
     }
 }
 
+// ---- contraction of a big tensor with a tiny one over ONE index (+ the complex component) -----------------------------
+// The state folding of the large-bond sweep: Bs[c,e,f] = sum_d G[c,d,e,f] s[d] (tneq_qc/contractor/greedy_strategy.py:
+// the circuit-state operands of every group, "cdef,...,d,i->..."), complex data in the 2x2-real form:
+//     out[a, c, ro] = sum_{d, ri} P[a, d, c, ri] * Q[d, ri, ro]          P: [A][D][C][2] in place, Q: [D][2][2]
+// The generic route was transposition (2 x 134 MB at bond 64) + a GEMM with N = 2 (a 128-wide tensor-core tile for two
+// columns); here P is read ONCE, coalesced along c, Q sits in shared memory.
+__global__ void __launch_bounds__(256) fold_vec_kernel(const float* __restrict__ P, const float* __restrict__ Q,
+                                                      float* __restrict__ out, long long A, int D, long long C) {
+    extern __shared__ float q[];                     // [D][4]
+    for (int i = threadIdx.x; i < D * 4; i += blockDim.x) q[i] = __ldg(Q + i);
+    __syncthreads();
+    const long long total = A * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long a = i / C, c = i - a * C;
+        const float2* src = reinterpret_cast<const float2*>(P) + a * D * C + c;
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < D; ++d) {
+            const float2 v = __ldg(src + (long long)d * C);
+            o0 = fmaf(v.x, q[4 * d], fmaf(v.y, q[4 * d + 2], o0));
+            o1 = fmaf(v.x, q[4 * d + 1], fmaf(v.y, q[4 * d + 3], o1));
+        }
+        reinterpret_cast<float2*>(out)[i] = make_float2(o0, o1);
+    }
+}
+
+// the adjoint (an outer product accumulated in place): T[a, d, c, ri] += sum_ro P[a, c, ro] * Q[d, ri, ro]
+__global__ void __launch_bounds__(256) outer_acc_kernel(const float* __restrict__ P, const float* __restrict__ Q,
+                                                       float* __restrict__ T, long long A, int D, long long C) {
+    extern __shared__ float q[];                     // [D][4]
+    for (int i = threadIdx.x; i < D * 4; i += blockDim.x) q[i] = __ldg(Q + i);
+    __syncthreads();
+    const long long total = A * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long a = i / C, c = i - a * C;
+        const float2 p = __ldg(reinterpret_cast<const float2*>(P) + i);
+        float2* dst = reinterpret_cast<float2*>(T) + a * D * C + c;
+#pragma unroll 8
+        for (int d = 0; d < D; ++d) {
+            float2 t = dst[(long long)d * C];
+            t.x = fmaf(p.x, q[4 * d], fmaf(p.y, q[4 * d + 1], t.x));
+            t.y = fmaf(p.x, q[4 * d + 2], fmaf(p.y, q[4 * d + 3], t.y));
+            dst[(long long)d * C] = t;
+        }
+    }
+}
+
 int fill_dims(Dims& d, int ndim, const int64_t* out_dims, const int64_t* in_strides) {
     if (ndim < 1 || ndim > MAXD) return tnq_internal_fail("tnq_permute: between 1 and 12 dimensions are supported");
     d.nd = ndim;
@@ -399,6 +446,26 @@ int tnq_cplx_fold_f32(const float* in, float* out, int ndim, const int64_t* out_
     tnq_internal_count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_cplx_fold_f32 launch");
+    return 0;
+}
+
+int tnq_fold_vec_f32(const float* P, const float* Q, float* out, int64_t A, int64_t D, int64_t C, void* stream) {
+    if (!P || !Q || !out || A <= 0 || D <= 0 || C <= 0 || D > 4096) return tnq_internal_fail("tnq_fold_vec_f32: bad arguments");
+    if (((uintptr_t)P | (uintptr_t)out) & 7) return tnq_internal_fail("tnq_fold_vec_f32: pointers must be 8-byte aligned");
+    fold_vec_kernel<<<grid_for(A * C, 256), 256, sizeof(float) * 4 * (size_t)D, (cudaStream_t)stream>>>(P, Q, out, A, (int)D, C);
+    tnq_internal_count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_fold_vec_f32 launch");
+    return 0;
+}
+
+int tnq_outer_acc_f32(const float* P, const float* Q, float* T, int64_t A, int64_t D, int64_t C, void* stream) {
+    if (!P || !Q || !T || A <= 0 || D <= 0 || C <= 0 || D > 4096) return tnq_internal_fail("tnq_outer_acc_f32: bad arguments");
+    if (((uintptr_t)P | (uintptr_t)T) & 7) return tnq_internal_fail("tnq_outer_acc_f32: pointers must be 8-byte aligned");
+    outer_acc_kernel<<<grid_for(A * C, 256), 256, sizeof(float) * 4 * (size_t)D, (cudaStream_t)stream>>>(P, Q, T, A, (int)D, C);
+    tnq_internal_count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_outer_acc_f32 launch");
     return 0;
 }
 

@@ -14,6 +14,8 @@ cores wider than TNQ_SGDG_MAX_COLS go through torch on the device.
 """
 from __future__ import annotations
 
+import functools
+import math
 import random
 from typing import Any, Dict, List, Tuple
 
@@ -109,10 +111,13 @@ def _rmsprop(params, grads, state, hp):
 SGDG_MAX_COLS = 64          # TNQ_SGDG_MAX_COLS, include/tneq_b200.h
 
 
+@functools.lru_cache(maxsize=4096)
 def _matrix_shape(shp):
+    """(rows, columns) of a core seen as the matrix the Cayley step works on (backend_pytorch.py:392-399); cached:
+    one call per core and step sat at 10 % of a candidate's host time in the population benchmark."""
     if len(shp) > 2:
-        rows = int(np.prod(shp[: len(shp) // 2]))
-        return rows, int(np.prod(shp)) // max(rows, 1)
+        rows = math.prod(int(x) for x in shp[: len(shp) // 2])
+        return rows, math.prod(int(x) for x in shp) // max(rows, 1)
     return (int(shp[0]), int(shp[1])) if len(shp) == 2 else (0, 0)
 
 

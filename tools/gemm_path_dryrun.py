@@ -32,6 +32,14 @@ class FakeLib:
     def tnq_cplx_fold_f32(self, src, dst, k, dims, *rest):
         return self._elementwise("fold", dims, k)
 
+    def tnq_fold_vec_f32(self, P, Q, out, A, D, C, stream):
+        self.log.append(("foldvec", (A * D * C * 2 + A * C * 2) * 4 / 2, [A, D, C], [], 0))
+        return 0
+
+    def tnq_outer_acc_f32(self, P, Q, T, A, D, C, stream):
+        self.log.append(("outeracc", (A * D * C * 2 * 2 + A * C * 2) * 4 / 2, [A, D, C], [], 0))
+        return 0
+
     def tnq_gemm_tf32x3_view(self, A, R1, R0, sR1, sR0, K1, K0, sK1, B, ldb, C, ldc, N, stream):
         ok = K0 % 32 == 0 and (R0 % 128 == 0 or 128 % R0 == 0) and K1 * K0 > 256 and not (sR1 % 4 or sR0 % 4 or sK1 % 4)
         if ok:
