@@ -376,6 +376,29 @@ def main():
         flat /= world
         return flat
 
+    # GB-sized gradients (cfg4: 15 cores x 134 MB): every core's all-reduce starts on a side stream as soon as that
+    # core's gradient is final (the reverse sweep finishes the cores in reverse-use order) and runs under the rest
+    # of the sweep; the step then only waits for the last one (reference: one blocking collective per core AFTER the
+    # backward pass, comm_torch.py:292-318, 510-522)
+    overlap = {"on": False, "checked": False}
+    if dist is not None and train and oneshot is None and hasattr(fn, "set_grad_ready_hook") and not args.nccl_allreduce:
+        comm_stream = torch.cuda.Stream(device=dev)
+        overlap["on"] = True
+
+        def grad_ready(name, flat):
+            comm_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(comm_stream):
+                dist.all_reduce(flat)
+                flat.div_(world)
+
+        def average_overlapped(loss, grads):
+            """all core gradients are already being reduced in place; only the loss is left"""
+            l = loss.detach().reshape(1).clone()
+            dist.all_reduce(l)
+            l /= world
+            torch.cuda.current_stream(dev).wait_stream(comm_stream)
+            return l
+
     if dist is not None and train and oneshot is not None and not args.no_graphs:
         # the exchange is recorded into the training step's CUDA graph: a step is one graph launch
         fn.set_graph_epilogue(lambda loss0, grads: average(loss0, grads))
@@ -383,13 +406,33 @@ def main():
     def step_device():
         if train:
             loss, grads, _vals, _sc = fn.loss_and_grads(cores_dict, states, mx_dev)
-            if dist is not None and fn.graph_stats["last_extra"] is None:
-                average(loss, grads)
+            if dist is not None:
+                if overlap["on"]:
+                    average_overlapped(loss, grads)
+                elif fn.graph_stats["last_extra"] is None:
+                    average(loss, grads)
             return loss
         with torch.no_grad():
             if wl["mode"] == "fwdx":
                 return engine.contract_from_x(qctn, states, x_dev, K=K)
             return fn(cores_dict, states, mx_dev).tensor
+
+    if overlap["on"]:
+        # once, on the ranks that are about to be timed: the overlapped per-core exchange must give what ONE packed NCCL
+        # all-reduce after the step gives (the cores are not updated in between)
+        real = lambda g: torch.view_as_real(g).reshape(-1) if g.is_complex() else g.reshape(-1)
+        loss_a, grads_a, _v, _s = fn.loss_and_grads(cores_dict, states, mx_dev)
+        want = average(loss_a, grads_a)
+        want = torch.cat([real(want[:-1]), want[-1:].real.reshape(1)]) if want.is_complex() else want
+        del grads_a
+        fn.set_grad_ready_hook(grad_ready)
+        loss_b, grads_b, _v, _s = fn.loss_and_grads(cores_dict, states, mx_dev)
+        l_b = average_overlapped(loss_b, grads_b)
+        got = torch.cat([real(g) for g in grads_b] + [l_b.reshape(1).float()])
+        err = (got - want.float()).abs().max().item() / max(want.abs().max().item(), 1e-30)
+        assert err <= 1e-5, f"overlapped per-core all-reduce disagrees with the packed one: {err}"
+        overlap["checked"], overlap["err"] = True, err
+        del want, got, grads_b
 
     x_dev = x_local.to(dev).contiguous()
     use_graphs = train and not args.no_graphs
@@ -458,7 +501,9 @@ def main():
             loss, grads = engine.contract_with_compiled_strategy_for_gradient(qctn, states, mxs)
             if dist is not None:
                 avg = fn.graph_stats["last_extra"]          # the exchange ran inside the step's graph ...
-                if avg is None:
+                if overlap["on"]:
+                    avg = average_overlapped(loss, grads)   # ... or core by core under the reverse sweep (cfg4) ...
+                elif avg is None:
                     avg = average(loss, grads)              # ... or the step was launched directly
                 val = read_back(avg[-1])
             else:
@@ -626,9 +671,13 @@ def main():
                        "cuda_graphs": bool(not args.no_graphs and (bound.ladder or bound.chain_rank) and wl["mode"] != "fwdx"),
                        "parallelism": f"batch sharded over {world} GPU(s); cores replicated; "
                                       + (("one one-shot NVLink all-reduce (tnq_allreduce_oneshot, symmetric memory) of grads+loss per step"
-                                          if oneshot is not None else "one packed NCCL all-reduce of grads+loss per step")
+                                          if oneshot is not None else
+                                          ("NCCL all-reduce per core, started when the core's gradient is final and overlapped with "
+                                           "the rest of the reverse sweep" if overlap["on"] else
+                                           "one packed NCCL all-reduce of grads+loss per step"))
                                          if world > 1 else "no collective"),
-                       "oneshot_vs_nccl_rel_err": checked.get("err_vs_nccl")},
+                       "oneshot_vs_nccl_rel_err": checked.get("err_vs_nccl"),
+                       "overlapped_vs_packed_rel_err": overlap.get("err")},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
     if wl["mode"] == "fwdx":
         # the same job without the fusion: x -> generate_data (torch, device) -> contraction, timed the same way

@@ -365,7 +365,12 @@ class _Call:
 
     def _gemm_backward(self, cores, seed):
         r = self.bound.gemm_runner("bwd")
-        val, lay = r.run(self._gemm_inputs(cores), self.B, self.nb, with_adjoint=True, seed=seed)
+        hook = getattr(self.bound, "grad_hook", None)
+        ready = None
+        if hook is not None:
+            names = {key: key[1] for key in self.core_keys}
+            ready = lambda key, flat: hook(names.get(key, key), flat)
+        val, lay = r.run(self._gemm_inputs(cores), self.B, self.nb, with_adjoint=True, seed=seed, on_grad_ready=ready)
         grads = []
         for key, c in zip(self.core_keys, cores):
             gflat = val[r.g.grads[key]]
@@ -472,6 +477,7 @@ class B200Strategy(ContractionStrategy):
 
     def get_compute_function(self, qctn, shapes_info: Dict[str, Any], backend, right_qctn="symmetric") -> Callable:
         plans: Dict[Any, _Bound] = {}
+        hooks = {"grad_ready": None}          # set_grad_ready_hook
         tnt_cls = self.tntensor_cls
         nq = qctn.nqubits
         table = qctn.adjacency_table
@@ -568,6 +574,7 @@ class B200Strategy(ContractionStrategy):
                 plan = ContractionPlan(table, nq, shapes, state_dims, mx_info, _DTYPE_NAME[dtype], right=right_mode,
                                        right_table=right_table, right_core_shapes=rshapes)
                 bound = plans[key] = _Bound(plan, device)
+            bound.grad_hook = hooks["grad_ready"]
             call = _Call(bound, core_keys, states, mxs, B, dtype)
             return call, cores, _scale_of(bound, tnt)
 
@@ -763,6 +770,16 @@ class B200Strategy(ContractionStrategy):
                 graphs["entries"].clear()
                 graphs["seen"].clear()
 
+        def set_grad_ready_hook(fn_or_none):
+            """fn(core name, flat float32 real view of that core's gradient), called DURING the reverse sweep of the
+            large-bond route as soon as the gradient of a core is final (reverse-use order): data-parallel training
+            starts the core's all-reduce on a side stream there, so that the exchange of the GB-sized gradients runs
+            under the rest of the sweep (bench.py --workload cfg4 --gpus N).  The fused small-bond kernels produce all
+            gradients at once (one 15 KB exchange, set_graph_epilogue); None removes the hook."""
+            hooks["grad_ready"] = fn_or_none
+            for b in plans.values():
+                b.grad_hook = fn_or_none
+
         def set_graph_epilogue(fn_or_none):
             """fn(loss0, grads) -> anything, called INSIDE the capture of the fused training step, right after
             its launches (data-parallel training records its gradient exchange there).  After every call of
@@ -874,6 +891,7 @@ class B200Strategy(ContractionStrategy):
         compute_fn.loss_and_grads = loss_and_grads
         compute_fn.enable_cuda_graphs = enable_cuda_graphs
         compute_fn.set_graph_epilogue = set_graph_epilogue
+        compute_fn.set_grad_ready_hook = set_grad_ready_hook
         compute_fn.graph_stats = graphs
         compute_fn.equations = equations
         compute_fn.forward_from_x = forward_from_x

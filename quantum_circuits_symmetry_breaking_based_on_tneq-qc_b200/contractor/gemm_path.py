@@ -202,11 +202,24 @@ class GemmPathRunner:
 
     # ---- node execution ----------------------------------------------------------------------
     def run(self, inputs: Dict[Tuple[str, object], torch.Tensor], B: int, nb: int, with_adjoint: bool,
-            seed=None):
+            seed=None, on_grad_ready=None):
         """inputs: real-view fp32 tensors per input key (batched ones with the sample dimension
-        first, nsamples = B * nb).  Returns (values dict, layouts dict)."""
+        first, nsamples = B * nb).  Returns (values dict, layouts dict).
+        on_grad_ready(core key, flat real-view gradient): called as soon as a core's gradient is FINAL (all its
+        contributions accumulated), in reverse-use order of the cores -- data-parallel training starts that core's
+        all-reduce on a side stream there, under the rest of the reverse sweep (the reference reduces every core
+        after the backward pass, tneq_qc/distributed/comm/comm_torch.py:292-318, 510-522)."""
         g = self.g
         NS = B * nb
+        fire = {}
+        if on_grad_ready is not None and with_adjoint:
+            final_at = {}
+            for pos, m in enumerate(g.nodes):
+                final_at[m.id] = max(final_at.get(m.id, -1), pos)
+                if m.acc_into >= 0:
+                    final_at[m.acc_into] = max(final_at.get(m.acc_into, -1), pos)
+            for key, nid in g.grads.items():
+                fire.setdefault(final_at[nid], []).append((key, nid))
         val: Dict[int, torch.Tensor] = {}
         lay: Dict[int, List[int]] = {}
         # look-ahead: the indices a node's consumer will contract (so the producer can emit them
@@ -219,41 +232,48 @@ class GemmPathRunner:
                 self._knext.setdefault(p_.id, sh)
                 self._knext.setdefault(q_.id, sh)
 
-        for n in g.nodes:
-            if n.role == "adj" and not with_adjoint:
-                continue
-            if n.kind == "input":
-                key = (n.operand.kind, n.operand.key)
-                if key[0] == "gradseed":     # d loss / d result: a tensor, or a callable of the forward result
-                    t = seed(val[g.result], lay[g.result]) if callable(seed) else seed
-                else:
-                    t = inputs[key]
-                val[n.id] = t
-                lay[n.id] = ([BATCH] if n.batched else []) + list(n.idx)
-                continue
-            if n.is_accum:
-                val[n.id] = torch.zeros(tuple(g.dims[i] for i in n.idx) or (1,), dtype=torch.float32, device=self.device)
-                lay[n.id] = list(n.idx)
-                continue
-            if n.kind == "seed":
-                raise NotImplementedError("fused loss is not part of the GEMM path (autograd route only)")
-            if n.kind == "lin":
-                out, out_layout = self._lin(n, val, lay, NS)
-            else:
-                if self._outer_acc(n, val, lay):
-                    continue
-                fused = self._fold_vec(n, val, lay)
-                out, out_layout = fused if fused is not None else self._contract(n, val, lay, NS)
-            if n.acc_into >= 0:
-                # a contribution is declared in the target's memory order (its own labels: a core's
-                # L and R occurrences carry different index ids over the same buffer)
-                tgt = val[n.acc_into]
-                if out_layout != list(n.idx):
-                    out, _ = self._arrange(out, out_layout, list(n.idx), [], NS, exact=True)
-                tgt.add_(out.reshape(tgt.shape))
-            else:
-                val[n.id], lay[n.id] = out, out_layout
+        for pos, n in enumerate(g.nodes):
+            self._run_node(n, val, lay, inputs, NS, with_adjoint, seed)
+            for key, nid in fire.get(pos, ()):
+                on_grad_ready(key, val[nid])
         return val, lay
+
+    def _run_node(self, n: Node, val, lay, inputs, NS, with_adjoint, seed):
+        """Execute one node of the graph (values and layouts are recorded in val / lay)."""
+        g = self.g
+        if n.role == "adj" and not with_adjoint:
+            return
+        if n.kind == "input":
+            key = (n.operand.kind, n.operand.key)
+            if key[0] == "gradseed":     # d loss / d result: a tensor, or a callable of the forward result
+                t = seed(val[g.result], lay[g.result]) if callable(seed) else seed
+            else:
+                t = inputs[key]
+            val[n.id] = t
+            lay[n.id] = ([BATCH] if n.batched else []) + list(n.idx)
+            return
+        if n.is_accum:
+            val[n.id] = torch.zeros(tuple(g.dims[i] for i in n.idx) or (1,), dtype=torch.float32, device=self.device)
+            lay[n.id] = list(n.idx)
+            return
+        if n.kind == "seed":
+            raise NotImplementedError("fused loss is not part of the GEMM path (autograd route only)")
+        if n.kind == "lin":
+            out, out_layout = self._lin(n, val, lay, NS)
+        else:
+            if self._outer_acc(n, val, lay):
+                return
+            fused = self._fold_vec(n, val, lay)
+            out, out_layout = fused if fused is not None else self._contract(n, val, lay, NS)
+        if n.acc_into >= 0:
+            # a contribution is declared in the target's memory order (its own labels: a core's
+            # L and R occurrences carry different index ids over the same buffer)
+            tgt = val[n.acc_into]
+            if out_layout != list(n.idx):
+                out, _ = self._arrange(out, out_layout, list(n.idx), [], NS, exact=True)
+            tgt.add_(out.reshape(tgt.shape))
+        else:
+            val[n.id], lay[n.id] = out, out_layout
 
     def _lin(self, n: Node, val, lay, NS):
         g = self.g
