@@ -48,6 +48,9 @@ class TrainingConfig:
     momentum: float = 0.9
     stiefel: bool = True
     seed: int = 42
+    # (no reference counterpart) large-bond route: start every core's all-reduce when its gradient is final, under the
+    # rest of the reverse sweep, instead of one exchange after the step
+    overlap_exchange: bool = True
 
 
 @dataclass
@@ -78,6 +81,7 @@ class DataParallelTrainer:
         self.accumulation_count = 0
         self._oneshot, self._oneshot_tried = None, False
         self._graphs, self._epi_fn, self._ls_dev = False, None, None
+        self._ovl_fn, self._ovl = None, None
         # lock-step QR retractions on every rank: a private stream, not the process-global one
         self.optimizer.opt_state["rng"] = random.Random(self.config.seed)
 
@@ -154,6 +158,32 @@ class DataParallelTrainer:
         out = self.comm.allreduce_list(list(grads) + [loss_t], op=ReduceOp.AVG)
         return out[:-1], out[-1][0]
 
+    def _overlap_for(self, fn) -> bool:
+        """Large-bond route (GB-sized gradients, e.g. 15 cores x 134 MB at bond 64): every core's NCCL all-reduce is
+        started on a side stream by compute_fn.set_grad_ready_hook as soon as that core's gradient is final -- the
+        reverse sweep finishes the cores in reverse-use order -- and overlaps the rest of the sweep.  The reference
+        issues one blocking collective per core after the backward pass (comm_torch.py:292-318, 510-522)."""
+        if not (self.config.overlap_exchange and self.world_size > 1 and hasattr(fn, "set_grad_ready_hook")
+                and self.comm.device.type == "cuda"):
+            return False
+        if self._ovl_fn is not fn:
+            import torch.distributed as dist
+            stream = torch.cuda.Stream(device=self.comm.device)
+            state = {"fired": 0, "stream": stream}
+            world = self.world_size
+
+            def ready(name, flat):
+                stream.wait_stream(torch.cuda.current_stream(flat.device))
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(flat)
+                    flat.div_(world)
+                state["fired"] += 1
+
+            fn.set_grad_ready_hook(ready)
+            self._ovl_fn, self._ovl = fn, state
+        self._ovl["fired"] = 0
+        return True
+
     def enable_cuda_graphs(self, flag: bool = True):
         """One CUDA-graph launch per training step (no reference counterpart): the fused contraction kernels
         AND the one-shot NVLink exchange of gradients + loss are captured together (the engine's graph replay,
@@ -216,7 +246,20 @@ class DataParallelTrainer:
                          if m is not None)
                 ls += sum(float(w.log_scale) for w in self.qctn.cores_weights.values() if hasattr(w, "log_scale"))
                 self._ls_dev.fill_(ls)
+        overlapping = False
+        if (k == 1 and self.world_size > 1 and "measure_input_list" in data and self.config.overlap_exchange
+                and self.comm.device.type == "cuda" and hasattr(self.engine, "_compiled")):
+            ofn = fn if fn is not None else self.engine._compiled(
+                self.qctn, circuit_states_list, data["measure_input_list"], data.get("measure_is_matrix", True), "symmetric")
+            overlapping = self._overlap_for(ofn)
         loss, grads = self.compute_local_gradients(data, circuit_states_list)
+        if overlapping and self._ovl["fired"] == len(grads) and len(grads):
+            # every core's gradient was averaged in place while the sweep was still running: wait for the last one
+            torch.cuda.current_stream(self.comm.device).wait_stream(self._ovl["stream"])
+            self.optimizer.step(self.qctn, list(grads))
+            loss_avg = self.sync_loss(float(loss))
+            self.optimizer.iter += 1
+            return loss_avg
         if fn is not None and self._epi_fn is fn and fn.graph_stats["last_extra"] is not None:
             out = fn.graph_stats["last_extra"]             # exchange done inside the step's graph
             pieces, at = [], 0

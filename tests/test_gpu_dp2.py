@@ -119,3 +119,78 @@ def test_two_gpu_training_matches_single_process_schedule(built_lib, tmp_path):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("DP2-OK") == 2
+
+
+WORKER_OVERLAP = r'''
+import os, sys
+os.environ["TNQ_FORCE_GEMM_PATH"] = "1"          # the route bond 64-128 takes, at a size that runs in seconds
+sys.path.insert(0, os.environ["TNQ_ROOT"]); sys.path.insert(0, os.path.join(os.environ["TNQ_ROOT"], "tests"))
+import torch, torch.distributed as dist
+import tneq_b200 as tb
+from tneq_b200.distributed import NcclComm, DataParallelTrainer, TrainingConfig
+from oracle import qctn_oracle as oc
+
+rank = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+comm = NcclComm(backend="nccl", device=dev)
+n, K, B, STEPS = 5, 8, 12, 3
+graph = tb.QCTNHelper.generate_example_graph(n=n, graph_type="mps", dim_char=str(K))
+names, table, nq = oc.parse_graph(graph)
+torch.manual_seed(11)
+cores0 = oc.random_cores(table, torch.complex64)
+mats = []
+for r in range(2):                                # one batch per rank, identical on both ranks
+    ms = []
+    for q_ in range(nq):
+        v = torch.randn(B, K, dtype=torch.complex64)
+        ms.append(torch.einsum("bi,bj->bij", v.conj(), v) / K)
+    mats.append(ms)
+
+
+def run(overlap):
+    be = tb.BackendFactory.create_backend("b200", device=str(dev), dtype="complex64")
+    eng = tb.EngineSiamese(backend=be, strategy_mode="balanced", mx_K=K)
+    q = tb.QCTN(graph, backend=be)
+    for k, v in cores0.items():
+        q.cores_weights[k] = v.to(dev).clone().requires_grad_(True)
+    st = [s.to(dev).to(torch.complex64) for s in oc.unit_states(nq, K)]
+    data = [{"measure_input_list": [m.to(dev).contiguous() for m in ms]} for ms in mats]
+    cfg = TrainingConfig(optimizer_method="sgd", learning_rate=0.05, log_interval=0, tol=0.0, seed=9, overlap_exchange=overlap)
+    tr = DataParallelTrainer(eng, q, cfg, comm=comm)
+    mine = tr.partition_data(data)
+    tr.sync_model_weights()
+    losses = [tr.train_step(mine[0], st) for _ in range(STEPS)]
+    fired = tr._ovl["fired"] if tr._ovl is not None else 0
+    return losses, torch.cat([torch.view_as_real(q.cores_weights[c].detach()).reshape(-1) for c in q.cores]), fired, len(q.cores)
+
+
+la, ca, fired, ncores = run(True)
+assert fired == ncores, (fired, ncores)           # every core was reduced from inside the reverse sweep
+lb, cb, fired_b, _ = run(False)
+assert fired_b == 0
+err = ((ca - cb).abs().max() / cb.abs().max()).item()
+assert err < 1e-6, f"overlapped per-core exchange differs from the packed exchange: {err:.2e}"
+for a, b in zip(la, lb):
+    assert abs(a - b) <= 1e-6 * abs(b), (a, b)
+both = [torch.empty_like(ca) for _ in range(2)]
+dist.all_gather(both, ca)
+assert torch.equal(both[0], both[1]), "replicas diverged"
+comm.barrier()
+comm.destroy()
+print("DP2-OVERLAP-OK", rank, err)
+'''
+
+
+def test_two_gpu_large_bond_exchange_overlaps_the_reverse_sweep(built_lib, tmp_path):
+    """DataParallelTrainer on the large-bond (GEMM) route: every core's all-reduce is started from inside the reverse
+    sweep (compute_fn.set_grad_ready_hook) -- same cores and losses as the packed exchange after the step."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "dp2_overlap_worker.py"
+    script.write_text(WORKER_OVERLAP)
+    env = dict(os.environ, TNQ_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29539", str(script)],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
