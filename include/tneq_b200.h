@@ -170,6 +170,16 @@ int tnq_gemm_tf32x3(const float* A, const float* B, float* C, int64_t M, int64_t
 /* Launch resources of one variant of the GEMM kernel: out[4] = {registers per thread, max threads per block,
  * static shared bytes, threads per block the launch uses}. */
 /*
+ * Batch-into-K GEMM (the gradients of shared tensors: the sample index joins the contracted indices,
+ * torch.autograd through torch.einsum in the reference, tneq_qc/core/engine_siamese.py:476,537):
+ *   C[m, n] = sum_{b, k} A_b[m, k] * B_b[n, k],  K = batch x Kin.
+ * An operand is K-major and contiguous, X[rows][batch * Kin] (x_mn = 0), or MN-major IN PLACE,
+ * X[batch][x_tiles][Kin][128] with rows = 128 x_tiles (x_mn = 1): read through a 5-D tensor map and consumed by the
+ * tensor core through MN-major shared-memory descriptors, i.e. without the transposition.  -2: not expressible, nothing launched.
+ */
+int tnq_gemm_tf32x3_bk(const float* A, int a_mn, int64_t a_tiles, const float* B, int b_mn, int64_t b_tiles, float* C,
+                       int64_t M, int64_t N, int64_t batch, int64_t Kin, void* stream);
+/*
  * Contraction of a big tensor with a tiny one over ONE index and the complex component -- the circuit-state operands
  * of every greedy group ("cdef,...,d,i->...": Bs[c,e,f] = sum_d G[c,d,e,f] s[d], tneq_qc/contractor/greedy_strategy.py:690-990)
  * at large bond dimension, complex data in the 2x2-real form -- and its adjoint, both in ONE pass over the big tensor

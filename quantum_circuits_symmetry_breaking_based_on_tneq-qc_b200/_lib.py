@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtneq_b200.so")
 
 EXPORTS = ["tnq_device_check", "tnq_plan_create", "tnq_plan_destroy", "tnq_plan_num_inputs",
-           "tnq_plan_num_outputs", "tnq_plan_query", "tnq_plan_run", "tnq_gemm_tf32x3", "tnq_gemm_tf32x3_view", "tnq_gemm_kernel_attrs", "tnq_permute_f32", "tnq_fold_vec_f32", "tnq_outer_acc_f32", "tnq_cplx_expand_f32",
+           "tnq_plan_num_outputs", "tnq_plan_query", "tnq_plan_run", "tnq_gemm_tf32x3", "tnq_gemm_tf32x3_view", "tnq_gemm_tf32x3_bk", "tnq_gemm_kernel_attrs", "tnq_permute_f32", "tnq_fold_vec_f32", "tnq_outer_acc_f32", "tnq_cplx_expand_f32",
            "tnq_cplx_fold_f32", "tnq_mps_chain", "tnq_mps_chain_workspace_bytes", "tnq_mps_chain_x", "tnq_mps_chain_sample", "tnq_mps_ladder",
            "tnq_mps_ladder_workspace_bytes", "tnq_mps_ladder2", "tnq_mps_ladder2_workspace_bytes", "tnq_mps_ladder2_geometry", "tnq_allreduce_oneshot", "tnq_allreduce_oneshot_words", "tnq_allreduce_set_timeout_ms", "tnq_sgdg_step", "tnq_sgdg_step_flat", "tnq_launch_count",
            "tnq_last_error"]
@@ -50,6 +50,8 @@ def load():
                                  POINTER(c_void_p), POINTER(c_double), c_void_p, c_int64, c_void_p]
     lib.tnq_gemm_tf32x3.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int64] * 10 + [c_int, c_void_p]
     lib.tnq_gemm_tf32x3_view.argtypes = [c_void_p] + [c_int64] * 7 + [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p]
+    lib.tnq_gemm_tf32x3_bk.argtypes = [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                                       c_int64, c_void_p]
     lib.tnq_fold_vec_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]
     lib.tnq_outer_acc_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]
     lib.tnq_permute_f32.argtypes = [c_void_p, c_void_p, c_int, POINTER(c_int64), POINTER(c_int64), c_int, c_int, c_void_p]

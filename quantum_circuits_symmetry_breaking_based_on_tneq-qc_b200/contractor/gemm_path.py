@@ -26,6 +26,8 @@ from .. import _lib
 from .cgraph import CGraph, Node
 
 BATCH = -1   # pseudo index id of the sample dimension in layouts
+# core-gradient GEMMs with MN-major operands read in place (tnq_gemm_tf32x3_bk); TNQ_GEMM_MN=0 transposes instead
+MN_IN_PLACE = __import__("os").environ.get("TNQ_GEMM_MN", "1") == "1"
 
 
 class GemmPathRunner:
@@ -130,6 +132,51 @@ class GemmPathRunner:
                                               c_void_p(tgt.data_ptr()), A, D, C, self._stream()))
         self.flops += 2.0 * A * D * C * 4
         return True
+
+    def _mn_in_place(self, layout: List[int], free: List[int], k: int, B: int):
+        """`layout` == [BATCH, hi..., k, lo...] with the lo indices spanning exactly one 128-row tile: the operand can be
+        consumed MN-major in place (tnq_gemm_tf32x3_bk).  Returns (row tiles, row order) or None."""
+        if not layout or layout[0] != BATCH or k not in layout:
+            return None
+        j = layout.index(k)
+        hi, lo = layout[1:j], layout[j + 1:]
+        if sorted(hi + lo) != sorted(free) or self._size(lo, B) != 128 or self._extent(k, B) % 32:
+            return None
+        return self._size(hi, B), hi + lo
+
+    def _reduce_in_place(self, tp, Lp, pf, tq, Lq, qf, shared, NS):
+        """C[pf, qf] = sum over (batch, k) with at least one operand read in place, MN-major (the 537 MB intermediates of
+        the bond-64 sweep are [batch][rows][k][128 rows]); the other operand is transposed explicitly when it is not of
+        that form (it is the small one).  None: not expressible, the caller transposes both."""
+        if len(shared) != 1 or not MN_IN_PLACE:
+            return None
+        k = shared[0]
+        a, b = self._mn_in_place(Lp, pf, k, NS), self._mn_in_place(Lq, qf, k, NS)
+        if a is None and b is None:
+            return None
+        Kin = self._extent(k, NS)
+        if NS * Kin <= 256:
+            return None
+        if a is None:
+            A, rows_a = self._arrange(tp, Lp, pf, [BATCH, k], NS)
+            a_tiles = 0
+        else:
+            A, (a_tiles, rows_a) = tp, a
+        if b is None:
+            Bm, rows_b = self._arrange(tq, Lq, qf, [BATCH, k], NS)
+            b_tiles = 0
+        else:
+            Bm, (b_tiles, rows_b) = tq, b
+        M, N = self._size(pf, NS), self._size(qf, NS)
+        C = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        rc = self.lib.tnq_gemm_tf32x3_bk(c_void_p(A.data_ptr()), int(a is not None), a_tiles, c_void_p(Bm.data_ptr()),
+                                         int(b is not None), b_tiles, c_void_p(C.data_ptr()), M, N, NS, Kin, self._stream())
+        if rc == -2:
+            return None
+        _lib.check(rc)
+        self.flops += 2.0 * M * N * NS * Kin
+        out_layout = rows_a + rows_b
+        return C.reshape([self.g.dims[i] for i in out_layout] or [1]), out_layout
 
     def _strided_view(self, layout: List[int], rows: List[int], cols: List[int], B: int):
         """`layout` read as rows x cols WITHOUT a copy, when memory order alternates as [rows][cols][rows][cols]
@@ -337,6 +384,9 @@ class GemmPathRunner:
         qf = [i for i in q.idx if i not in shared]
         if n.reduce_batch:
             # gradient of a shared tensor: the sample index joins the contracted indices (GEMM K)
+            fused = self._reduce_in_place(tp, Lp, pf, tq, Lq, qf, shared, NS)
+            if fused is not None:
+                return fused
             korder = self._tail_order(Lp, [BATCH] + shared)
             A, rows_a = self._arrange(tp, Lp, pf, korder, NS)
             Bm, rows_b = self._arrange(tq, Lq, qf, korder, NS)

@@ -105,14 +105,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128 (InstrDescriptor bit layout)
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t accumulate,
+                                          uint32_t idesc = IDESC) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
         "}\n" ::"r"(tmem_c),
-        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
 
@@ -404,6 +405,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 // UMMA shared-memory descriptor, K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
 // (SBO); LBO is not used by swizzled K-major layouts; a K=8 step advances the start address by 32 bytes inside
 // the swizzle atom (the hardware applies the XOR to the absolute address bits: tiles are 1024-byte aligned).
@@ -416,16 +423,36 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;   // SWIZZLE_128B
     return d;
 }
+// MN-major operand (the rows are the contiguous direction in memory: [k][128 rows]), 128-byte swizzle: atoms of 32 floats
+// (rows) x 8 k; the four row groups of a 128-row tile are LBO = 4096 bytes apart (one TMA box slice of 32 k-rows x 128 B),
+// groups of 8 k-rows SBO = 1024 bytes apart; a K = 8 step advances the start address by 1024 bytes.
+// (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>)
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t ltype) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(ltype & 7) << 61;
+    return d;
+}
+struct MnDesc {
+    uint32_t lbo, sbo, kstep, ltype;       // bytes, bytes, bytes per K = 8 step, UMMA layout type
+};
 __device__ __forceinline__ void issue_kblock_tma(uint32_t raw, uint32_t lo, uint32_t tmem_h, uint32_t tmem_corr, int kb, bool last,
-                                                 uint32_t done_bar, uint32_t accum_bar) {
+                                                 uint32_t done_bar, uint32_t accum_bar, int a_mn = 0, int b_mn = 0,
+                                                 MnDesc mn = MnDesc{4096, 512, 1024, 1}) {
+    const uint32_t idesc = IDESC | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
 #pragma unroll
     for (int j = 0; j < BK / 8; ++j) {
-        const uint32_t ko = (uint32_t)j * 32u;
-        const uint64_t a_hi = umma_desc_sw128(raw + ko), a_lo = umma_desc_sw128(lo + ko);
-        const uint64_t b_hi = umma_desc_sw128(raw + TILE_BYTES + ko), b_lo = umma_desc_sw128(lo + TILE_BYTES + ko);
-        umma_tf32(tmem_corr, a_lo, b_hi, (kb | j) != 0);
-        umma_tf32(tmem_corr, a_hi, b_lo, 1u);
-        umma_tf32(tmem_h, a_hi, b_hi, j != 0);
+        const uint32_t ka = (uint32_t)j * (a_mn ? mn.kstep : 32u), kb_ = (uint32_t)j * (b_mn ? mn.kstep : 32u);
+        const uint64_t a_hi = a_mn ? umma_desc_mn_sw128(raw + ka, mn.lbo, mn.sbo, mn.ltype) : umma_desc_sw128(raw + ka);
+        const uint64_t a_lo = a_mn ? umma_desc_mn_sw128(lo + ka, mn.lbo, mn.sbo, mn.ltype) : umma_desc_sw128(lo + ka);
+        const uint64_t b_hi = b_mn ? umma_desc_mn_sw128(raw + TILE_BYTES + kb_, mn.lbo, mn.sbo, mn.ltype) : umma_desc_sw128(raw + TILE_BYTES + kb_);
+        const uint64_t b_lo = b_mn ? umma_desc_mn_sw128(lo + TILE_BYTES + kb_, mn.lbo, mn.sbo, mn.ltype) : umma_desc_sw128(lo + TILE_BYTES + kb_);
+        umma_tf32(tmem_corr, a_lo, b_hi, (kb | j) != 0, idesc);
+        umma_tf32(tmem_corr, a_hi, b_lo, 1u, idesc);
+        umma_tf32(tmem_h, a_hi, b_hi, j != 0, idesc);
     }
     umma_commit(done_bar);
     if (last) umma_commit(accum_bar);
@@ -438,7 +465,10 @@ __global__ void __maxnreg__(SOLO ? 128 : 168)
 tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, int tma_store, float* __restrict__ C,
                     long long M, long long N, long long K, long long ldc, long long strideC, int zA, int zB, int accumulate,
-                    int rewrite_hi, int splitk, int a_r0, int a_kdiv) {
+                    int rewrite_hi, int splitk, int a_r0, int a_kdiv, int a_mn, int b_mn, int bk_kdiv, MnDesc mn) {
+    // a_mn / b_mn: the operand is MN-major IN PLACE, memory [batch][row tile][k (bk_kdiv blocks of 32)][128 rows], read
+    // through a 5-D tensor map (32-float chunk, k, chunk group, row tile, batch); the k-loop runs over (batch, k block):
+    // the batch-into-K contraction of the core gradients without the transposition (tnq_gemm_tf32x3_bk)
     // a_r0 > 0: A is a strided VIEW described by a 4-D tensor map (k0, r0, k1, r1) -- rows m = r1 * a_r0 + r0,
     // contraction index k = k1 * (32 a_kdiv) + k0: the index permutation an explicit transposition kernel would
     // do is done by the TMA unit while it fills the tile (tnq_gemm_tf32x3_view)
@@ -490,13 +520,16 @@ tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int sr = kb % NRAW;
         const uint32_t dst = raw0 + (uint32_t)sr * RAW_BYTES, bar = full_raw0 + 8 * sr;
         mbar_expect_tx(bar, RAW_BYTES);
-        if (a_r0 > 0) {
-            const int kk = kb0 + kb;
+        const int kk = kb0 + kb;
+        if (a_mn) {
+            tma_load_5d(dst, &tmA, bar, 0, (kk % bk_kdiv) * BK, 0, (int)(m0 / BM), kk / bk_kdiv);
+        } else if (a_r0 > 0) {
             tma_load_4d(dst, &tmA, bar, (kk % a_kdiv) * BK, a_r0 >= BM ? (int)(m0 % a_r0) : 0, kk / a_kdiv, (int)(m0 / a_r0));
         } else {
-            tma_load_3d(dst, &tmA, bar, (kb0 + kb) * BK, (int)m0, za);
+            tma_load_3d(dst, &tmA, bar, kk * BK, (int)m0, za);
         }
-        tma_load_3d(dst + TILE_BYTES, &tmB, bar, (kb0 + kb) * BK, (int)n0, zb);
+        if (b_mn) tma_load_5d(dst + TILE_BYTES, &tmB, bar, 0, (kk % bk_kdiv) * BK, 0, (int)(n0 / BN), kk / bk_kdiv);
+        else tma_load_3d(dst + TILE_BYTES, &tmB, bar, kk * BK, (int)n0, zb);
     };
 
     if (warp < PRODUCERS / 32) {
@@ -545,7 +578,7 @@ tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_wait(full_lo0 + 8 * sl, (uint32_t)(kb / NLO) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0)
-                    issue_kblock_tma(raw, lo, tmem_base + (uint32_t)(sl * BN), tmem_corr, kb, kb == nkb - 1, done0 + 8 * sr, accum_bar);
+                    issue_kblock_tma(raw, lo, tmem_base + (uint32_t)(sl * BN), tmem_corr, kb, kb == nkb - 1, done0 + 8 * sr, accum_bar, a_mn, b_mn, mn);
                 __syncwarp();
             }
         }
@@ -602,7 +635,7 @@ tnq_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0)
                 issue_kblock_tma(raw0 + (uint32_t)sr * RAW_BYTES, lo0 + (uint32_t)sl * RAW_BYTES, tmem_base + (uint32_t)(sl * BN), tmem_corr,
-                                 kb, kb == nkb - 1, done0 + 8 * sr, accum_bar);
+                                 kb, kb == nkb - 1, done0 + 8 * sr, accum_bar, a_mn, b_mn, mn);
             __syncwarp();
         }
     } else if (!SOLO) {
@@ -657,6 +690,12 @@ bool make_operand_map(CUtensorMap* map, const float* base, long long rows, long 
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// MN-major descriptor parameters (diagnostic overrides: TNQ_MN_LBO / _SBO / _KSTEP / _LTYPE / _TMASW)
+MnDesc mn_desc() {
+    auto env = [](const char* n, int dflt) { const char* v = getenv(n); return (uint32_t)(v ? atoi(v) : dflt); };
+    return MnDesc{env("TNQ_MN_LBO", 4096), env("TNQ_MN_SBO", 512), env("TNQ_MN_KSTEP", 1024), env("TNQ_MN_LTYPE", 1)};
+}
+
 // (k0, r0, k1, r1) view: element (m = r1 * R0 + r0, k = k1 * K0 + k0) at base + r1 sR1 + r0 sR0 + k1 sK1 + k0
 bool make_view_map(CUtensorMap* map, const float* base, long long R1, long long R0, long long sR1, long long sR0,
                    long long K1, long long K0, long long sK1) {
@@ -693,7 +732,7 @@ bool make_c_map(CUtensorMap* map, float* base, long long M, long long N, long lo
 template <int NRAW, int NLO, bool SOLO>
 int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long M, long long N, long long K, long long ldc,
                long long strideC, long long batch, int zA, int zB, int accumulate, int rewrite_hi, cudaStream_t st,
-               int a_r0 = 0, int a_kdiv = 1) {
+               int a_r0 = 0, int a_kdiv = 1, int a_mn = 0, int b_mn = 0, int bk_kdiv = 1) {
     // split-K by two when a long k-loop would leave more than half of the SMs without a tile (the core-gradient GEMMs
     // of the bond-64 sweep: 64 tiles, K = 16 384): C is zeroed, both halves add atomically
     int splitk = 1;
@@ -716,7 +755,7 @@ int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "cudaFuncSetAttribute(gemm tma)");
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)(splitk > 1 ? splitk : batch));
-    kern<<<grid, SOLO ? PRODUCERS : PRODUCERS + 64, smem, st>>>(ta, tb, tc, tma_store, C, M, N, K, ldc, strideC, zA, zB, accumulate, rewrite_hi, splitk, a_r0, a_kdiv);
+    kern<<<grid, SOLO ? PRODUCERS : PRODUCERS + 64, smem, st>>>(ta, tb, tc, tma_store, C, M, N, K, ldc, strideC, zA, zB, accumulate, rewrite_hi, splitk, a_r0, a_kdiv, a_mn, b_mn, bk_kdiv, mn_desc());
     tnq_internal_count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return tnq_internal_cuda_fail(e, "tnq_gemm_tf32x3 (TMA) launch");
@@ -790,4 +829,40 @@ extern "C" int tnq_gemm_tf32x3_view(const float* A, int64_t R1, int64_t R0, int6
     int zB = 0;
     if (!make_view_map(&ta, A, R1, R0, sR1, sR0, K1, K0, sK1) || !make_operand_map(&tb, B, N, K, ldb, 1, 0, &zB)) return -2;
     return launch_tma<4, 2, false>(ta, tb, C, M, N, K, ldc, 0, 1, 0, 0, 0, 0, (cudaStream_t)stream, (int)R0, (int)(K0 / BK));
+}
+
+
+namespace {
+// MN-major operand in place: memory [batch][tiles][Kin][128 rows]; (32-float chunk, k, chunk group, row tile, batch)
+bool make_mn_map(CUtensorMap* map, const float* base, long long tiles, long long Kin, long long batch) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc || ((uintptr_t)base & 15) || Kin % BK || tiles <= 0 || batch <= 0) return false;
+    const cuuint64_t dims[5] = {32, (cuuint64_t)Kin, 4, (cuuint64_t)tiles, (cuuint64_t)batch};
+    const cuuint64_t strides[4] = {128 * 4, 32 * 4, (cuuint64_t)Kin * 128 * 4, (cuuint64_t)tiles * Kin * 128 * 4};
+    const cuuint32_t box[5] = {32, (cuuint32_t)BK, 4, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    // 32-bit elements consumed MN-major need the 128-byte swizzle with 32-byte atoms (UMMA layout type SWIZZLE_128B_BASE32B)
+    const char* sw = getenv("TNQ_MN_TMASW");
+    const CUtensorMapSwizzle mode = (sw && atoi(sw) == 0) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, mode, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+/* Batch-into-K GEMM (the core gradients of the large-bond sweep): C[m, n] = sum_{b, k} A_b[m, k] * B_b[n, k], K = batch x Kin.
+ * An operand is either K-major and contiguous, X[rows][batch * Kin] (x_mn = 0), or MN-major IN PLACE, X[batch][x_tiles][Kin][128]
+ * with rows = x_tiles * 128 (x_mn = 1): the tensor the forward sweep produced, read through a 5-D tensor map and consumed
+ * by the tensor core through MN-major descriptors -- no transposition.  Returns -2 without launching when not expressible. */
+extern "C" int tnq_gemm_tf32x3_bk(const float* A, int a_mn, int64_t a_tiles, const float* B, int b_mn, int64_t b_tiles, float* C,
+                                  int64_t M, int64_t N, int64_t batch, int64_t Kin, void* stream) {
+    if (!A || !B || !C || M <= 0 || N <= 0 || batch <= 0 || Kin <= 0) return tnq_internal_fail("tnq_gemm_tf32x3_bk: bad arguments");
+    static const bool off = getenv("TNQ_GEMM_NO_TMA") != nullptr || getenv("TNQ_GEMM_NO_MN") != nullptr;
+    const long long K = batch * Kin;
+    if (off || K <= 256 || Kin % BK || (a_mn && M != a_tiles * BM) || (b_mn && N != b_tiles * BN)) return -2;
+    CUtensorMap ta, tb;
+    int z = 0;
+    if (!(a_mn ? make_mn_map(&ta, A, a_tiles, Kin, batch) : make_operand_map(&ta, A, M, K, K, 1, 0, &z))) return -2;
+    if (!(b_mn ? make_mn_map(&tb, B, b_tiles, Kin, batch) : make_operand_map(&tb, B, N, K, K, 1, 0, &z))) return -2;
+    return launch_tma<4, 2, false>(ta, tb, C, M, N, K, N, 0, 1, 0, 0, 0, 0, (cudaStream_t)stream, 0, 1, a_mn, b_mn, (int)(Kin / BK));
 }

@@ -42,13 +42,16 @@ def test_bond64_plan_data_movement():
     for e in views:
         R1, R0, sR1, sR0, K1, K0, sK1 = e[6][1:]
         assert (R1, R0, K1, K0) == (256, 64, 64, 128) and sR0 == K0 and sK1 == R0 * K0 and sR1 == K1 * sK1
+    # core gradients: the big operand is consumed MN-major in place, the batch joins the contraction index
+    bks = [e for e in r.log if e[0] == "gemm" and isinstance(e[6], tuple) and e[6] and e[6][0] == "bk"]
+    assert len(bks) == 6 and all(e[4] == 256 * 64 and (e[6][1] or e[6][2]) for e in bks)
     # circuit-state folding and its adjoint are the fused one-pass kernels, never a GEMM with two columns / K = 2
     assert kinds.count("foldvec") >= 2 * 4 and kinds.count("outeracc") >= 2 * 4
     assert not [e for e in r.log if e[0] == "gemm" and (e[3] == 2 or e[4] == 2) and e[2] >= 1 << 16]
     # no strided scalar transposition of a 537 MB tensor: every big permute has a long input-contiguous run after
     # merging neighbours (what tnq_permute_f32's canonicalisation needs for its tiled paths)
     moved = sum(e[1] for e in r.log if e[0] != "gemm")
-    assert 2 * moved < 25e9, 2 * moved / 1e9            # 40.3 GB before this round's changes, 22 GB now
+    assert 2 * moved < 12e9, 2 * moved / 1e9            # 40.3 GB before this round's changes, 9.1 GB now
     for e in r.log:
         if e[0] == "permute" and e[1] > 500e6:
             dims, strides = e[2], e[3]

@@ -99,3 +99,36 @@ def test_gemm_strided_view_operand(R1, R0, K1, K0, N, built_lib):
     assert lib.tnq_gemm_tf32x3_view(ctypes.c_void_p(X.data_ptr()), R1, R0, X.stride(0), X.stride(2), K1, K0 - 4, X.stride(1),
                                     ctypes.c_void_p(B.data_ptr()), K, ctypes.c_void_p(C.data_ptr()), N, N,
                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == -2
+
+
+@pytest.mark.parametrize("a_mn,b_mn,ta,tb,batch,Kin", [(1, 1, 1, 3, 5, 64), (1, 0, 2, 1, 9, 32), (0, 1, 1, 2, 4, 96), (1, 1, 1, 64, 256, 64)])
+def test_gemm_batch_into_k_mn_major_in_place(a_mn, b_mn, ta, tb, batch, Kin, built_lib):
+    """tnq_gemm_tf32x3_bk: C[m, n] = sum_{b, k} A_b[m, k] B_b[n, k] with operands stored [batch][row tile][k][128 rows]
+    consumed IN PLACE (5-D tensor map with the 32-byte-atom swizzle, MN-major UMMA descriptors of layout type
+    SWIZZLE_128B_BASE32B) -- the core-gradient contraction of the large-bond
+    sweep without the transposition -- against float64."""
+    from tneq_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(a_mn * 10 + b_mn + batch)
+    M, N = ta * 128, tb * 128
+
+    def operand(mn, tiles):
+        if mn:
+            x = torch.randn(batch, tiles, Kin, 128, device="cuda")                  # in place
+            ref = x.permute(1, 3, 0, 2).reshape(tiles * 128, batch * Kin)           # rows (tile, r), K (b, k)
+        else:
+            x = torch.randn(tiles * 128, batch * Kin, device="cuda")
+            ref = x
+        return x, ref.double()
+
+    A, Ar = operand(a_mn, ta)
+    B, Br = operand(b_mn, tb)
+    C = torch.empty(M, N, device="cuda")
+    rc = lib.tnq_gemm_tf32x3_bk(ctypes.c_void_p(A.data_ptr()), a_mn, ta, ctypes.c_void_p(B.data_ptr()), b_mn, tb,
+                                ctypes.c_void_p(C.data_ptr()), M, N, batch, Kin,
+                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    ref = Ar @ Br.T
+    err = ((C.double() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1e-5, err

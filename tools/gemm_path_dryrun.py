@@ -40,6 +40,11 @@ class FakeLib:
         self.log.append(("outeracc", (A * D * C * 2 * 2 + A * C * 2) * 4 / 2, [A, D, C], [], 0))
         return 0
 
+    def tnq_gemm_tf32x3_bk(self, A, a_mn, a_tiles, B, b_mn, b_tiles, C, M, N, batch, Kin, stream):
+        self.log.append(("gemm", 2.0 * M * N * batch * Kin, M, N, batch * Kin, 1, ("bk", a_mn, b_mn)))
+        print(f"  batch-into-K GEMM in place: M {M} N {N} K {batch * Kin} a_mn {a_mn} b_mn {b_mn}")
+        return 0
+
     def tnq_gemm_tf32x3_view(self, A, R1, R0, sR1, sR0, K1, K0, sK1, B, ldb, C, ldc, N, stream):
         ok = K0 % 32 == 0 and (R0 % 128 == 0 or 128 % R0 == 0) and K1 * K0 > 256 and not (sR1 % 4 or sR0 % 4 or sK1 % 4)
         if ok:
